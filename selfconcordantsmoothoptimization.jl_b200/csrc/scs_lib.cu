@@ -1,0 +1,1326 @@
+// scs_b200 — C-ABI host layer over the sm_100a kernels (see include/scs_b200.h for the contract and the
+// reference file:line each entry replaces).  One context per (process, GPU); all work of a context is issued on
+// its own stream; row-sharded problems reduce [g ‖ loss] and the Gram with NCCL fp64 sum all-reduces.
+#include "../../include/scs_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_gram.cuh"
+#include "kernels_solve.cuh"
+#include "kernels_stream.cuh"
+#include "kernels_vec.cuh"
+#include "nccl_dyn.hpp"
+#include "synth.cuh"
+
+using namespace scs;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(e_ == cudaErrorMemoryAllocation ? SCS_OOM : SCS_CUDA_ERROR,                     \
+                  std::string(#expr) + " failed: " + cudaGetErrorString(e_));                     \
+  } while (0)
+#define SCS_TRY(expr)          \
+  do {                         \
+    int s_ = (expr);           \
+    if (s_ != SCS_OK) return s_; \
+  } while (0)
+
+static NcclApi g_nccl;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum { ST_FWD = 0, ST_ADJ = 1, ST_GRAM = 2, ST_SOLVE = 3, ST_VEC = 4, ST_COMM = 5, ST_FUSED = 6, ST_N = 8 };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct scs_ctx {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  NcclComm comm = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool profiling = false;
+  double stage_ms[ST_N] = {0};
+  int64_t stage_calls[ST_N] = {0};
+  struct Pending {
+    int stage;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  EncodeTiledFn encode = nullptr;
+  // scratch for scs_linear_solve
+};
+
+struct StageTimer {  // records an event pair around a stage when profiling is on
+  scs_ctx* c;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(scs_ctx* c_, int s) : c(c_), stage(s) {
+    if (!c->profiling) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->ev_pool.empty()) {
+        e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, c->stream);
+  }
+  ~StageTimer() {
+    if (!c->profiling) return;
+    cudaEventRecord(b, c->stream);
+    c->pending.push_back({stage, a, b});
+  }
+};
+static void harvest_timers(scs_ctx* c) {  // call after a stream synchronize
+  for (auto& p : c->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      c->stage_ms[p.stage] += ms;
+      c->stage_calls[p.stage] += 1;
+    }
+    c->ev_pool.push_back(p.a);
+    c->ev_pool.push_back(p.b);
+  }
+  c->pending.clear();
+}
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                                   \
+  do {                                                                              \
+    kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);                        \
+    (ctx)->launches += 1;                                                           \
+    cudaError_t le_ = cudaGetLastError();                                           \
+    if (le_ != cudaSuccess)                                                         \
+      return fail(SCS_CUDA_ERROR, std::string(#kern) + " launch: " + cudaGetErrorString(le_)); \
+  } while (0)
+
+static int ctx_sync(scs_ctx* c) {
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  harvest_timers(c);
+  return SCS_OK;
+}
+
+static int allreduce(scs_ctx* c, double* buf, size_t count) {
+  if (c->world <= 1) return SCS_OK;
+  StageTimer t(c, ST_COMM);
+  int r = g_nccl.AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, c->comm, c->stream);
+  if (r != 0) return fail(SCS_NCCL_ERROR, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  double* p = nullptr;
+  size_t n = 0;
+};
+
+struct scs_problem {
+  scs_ctx* ctx = nullptr;
+  int64_t n = 0, m = 0, ldd = 0, mp = 0;  // mp = m rounded up to 16 (padded vector length)
+  double *dA = nullptr, *dy = nullptr, *dz = nullptr, *dr = nullptr, *dw = nullptr;
+  LossParams loss{};
+  // regulariser / smoother
+  bool has_reg = false, has_sm = false, has_method = false;
+  RegDesc reg{};
+  SmoothDesc sm{};
+  double Mh = 0, nu = 0;
+  double *d_rlb = nullptr, *d_rub = nullptr, *d_slb = nullptr, *d_sub = nullptr, *d_cdiag = nullptr;
+  int64_t *d_ind = nullptr, *d_perm = nullptr;
+  // method
+  int method = -1, ss_type = 1, use_prox = 1, lbfgs_m = 10;
+  bool has_L = false;
+  double L = 0;
+  // m-vectors (each mp doubles, zero padded)
+  double *vx[3] = {nullptr, nullptr, nullptr};  // rotating x buffers
+  double *d_gl = nullptr;                       // [g (m) ‖ loss sum (1)] all-reduce buffer, mp+16
+  double *d_gr = nullptr, *d_hr = nullptr, *d_rhs = nullptr, *d_sol = nullptr, *d_d = nullptr, *d_dx = nullptr,
+         *d_delta = nullptr, *d_gq = nullptr, *d_gqprev = nullptr, *d_gamma = nullptr, *d_q = nullptr,
+         *d_t1 = nullptr, *d_t2 = nullptr, *d_xstar = nullptr, *d_trial = nullptr, *d_gnewton = nullptr;
+  double* d_scal = nullptr;
+  double* h_scal = nullptr;  // pinned
+  // stream workspaces
+  int64_t fwd_blocks = 0, adj_blocks = 0;
+  double *d_losspart = nullptr, *d_adjpart = nullptr;
+  // gram / solve
+  double *d_G = nullptr, *d_Gsave = nullptr, *d_partial = nullptr, *d_Linv = nullptr;
+  int* d_info = nullptr;
+  GramPlan plan{};
+  int ldp = 0;
+  CUtensorMap amap{};
+  bool gram_ready = false;
+  // l-bfgs
+  double *d_S = nullptr, *d_Y = nullptr;
+  int64_t* d_state = nullptr;
+  int lbfgs_cap = 0;
+  // caches, keyed by x-vector ids
+  uint64_t next_id = 1;
+  uint64_t fwd_id = 0;
+  int fwd_wk = -1;
+  uint64_t grad_id = 0;  // d_gl[0..m) = allreduced A'r for this id (and fwd_wk)
+  uint64_t gq_id = 0;    // d_gq = ∇q at this id
+  uint64_t gqprev_id = 0;
+  bool loss_reduced = false;  // d_gl[m] already all-reduced for fwd_id
+  struct Shadow {
+    std::vector<double> x;
+    uint64_t id = 0;
+  };
+  Shadow shadow[4];
+  int shadow_next = 0;
+  int last_used_fallback = 0;
+};
+
+struct XRef {
+  double* d;
+  uint64_t id;
+};
+
+static int dalloc(double** p, size_t n) {
+  CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)));
+  CU_TRY(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(double)));
+  return SCS_OK;
+}
+static void dfree(void* p) {
+  if (p) cudaFree(p);
+}
+
+static int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// stream passes
+// ------------------------------------------------------------------------------------------------
+static int run_forward(scs_problem* p, const double* dx, int wk) {
+  scs_ctx* c = p->ctx;
+  StageTimer t(c, ST_FWD);
+  LossParams lp = p->loss;
+  lp.weight_kind = wk;
+  LAUNCH(c, k_forward<8>, (unsigned)p->fwd_blocks, kFwdThreads, 0, p->dA, p->ldd, p->n, (int)p->m, dx, p->dy, lp,
+         p->dz, p->dr, p->dw, p->d_losspart);
+  LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_losspart, p->fwd_blocks, p->d_gl + p->m);
+  return SCS_OK;
+}
+static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
+  scs_ctx* c = p->ctx;
+  StageTimer t(c, ST_ADJ);
+  LAUNCH(c, k_adjoint<8>, (unsigned)p->adj_blocks, kAdjThreads, 0, p->dA, p->ldd, (int)p->m, dr, p->d_adjpart);
+  LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_adjpart, p->adj_blocks, (int)p->m, dout);
+  return SCS_OK;
+}
+
+// forward pass at x (cached by id and weight kind); leaves z, r, w on the device and the local loss sum in d_gl[m]
+static int ensure_forward(scs_problem* p, XRef x, int wk) {
+  if (p->fwd_id == x.id && p->fwd_wk == wk) return SCS_OK;
+  SCS_TRY(run_forward(p, x.d, wk));
+  p->fwd_id = x.id;
+  p->fwd_wk = wk;
+  p->grad_id = 0;
+  p->loss_reduced = false;
+  return SCS_OK;
+}
+// loss sum all-reduced (objective only)
+static int ensure_loss(scs_problem* p, XRef x, int wk) {
+  SCS_TRY(ensure_forward(p, x, wk));
+  if (!p->loss_reduced) {
+    if (p->loss.kind == SCS_LOSS_QUADFORM) {
+      StageTimer t(p->ctx, ST_VEC);
+      LAUNCH(p->ctx, k_quadform_value, 1, kVecThreads, 0, x.d, p->dz, p->dy, (int)p->m, p->d_gl + p->m);
+    } else {
+      SCS_TRY(allreduce(p->ctx, p->d_gl + p->m, 1));
+    }
+    p->loss_reduced = true;
+  }
+  return SCS_OK;
+}
+// gradient of f at x into d_gl[0..m) (all-reduced together with the loss sum)
+static int ensure_grad(scs_problem* p, XRef x, int wk) {
+  SCS_TRY(ensure_forward(p, x, wk));
+  if (p->grad_id == x.id) return SCS_OK;
+  scs_ctx* c = p->ctx;
+  if (p->loss.kind == SCS_LOSS_QUADFORM) {
+    // g = 0.5*(A x + A' x) + y ; the adjoint pass takes r := x (zero padded to ldd)
+    CU_TRY(cudaMemsetAsync(p->dr, 0, p->ldd * sizeof(double), c->stream));
+    CU_TRY(cudaMemcpyAsync(p->dr, x.d, p->m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    SCS_TRY(run_adjoint(p, p->dr, p->d_t1));
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_quadform_grad, (unsigned)((p->m + 255) / 256), 256, 0, p->dz, p->d_t1, p->dy, (int)p->m, p->d_gl);
+    if (!p->loss_reduced) {
+      LAUNCH(c, k_quadform_value, 1, kVecThreads, 0, x.d, p->dz, p->dy, (int)p->m, p->d_gl + p->m);
+      p->loss_reduced = true;
+    }
+  } else {
+    SCS_TRY(run_adjoint(p, p->dr, p->d_gl));
+    if (!p->loss_reduced) {
+      SCS_TRY(allreduce(c, p->d_gl, p->m + 1));
+      p->loss_reduced = true;
+    } else {
+      SCS_TRY(allreduce(c, p->d_gl, p->m));
+    }
+  }
+  p->grad_id = x.id;
+  return SCS_OK;
+}
+
+static double fval_from_sum(const scs_problem* p, double S) {
+  switch (p->loss.kind) {
+    case SCS_LOSS_LOGISTIC:
+      return p->loss.p * S;
+    case SCS_LOSS_LEASTSQUARES:
+      return 0.5 * S / p->loss.p;
+    default:
+      return S;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gram + solve
+// ------------------------------------------------------------------------------------------------
+static int gram_setup(scs_problem* p) {
+  if (p->gram_ready) return SCS_OK;
+  scs_ctx* c = p->ctx;
+  const int64_t m = p->m;
+  SCS_TRY(dalloc(&p->d_G, (size_t)m * m));
+  SCS_TRY(dalloc(&p->d_Gsave, (size_t)m * m));
+  const int nblk = (int)((m + kNB - 1) / kNB);
+  SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB));
+  CU_TRY(cudaMalloc((void**)&p->d_info, sizeof(int)));
+  if (p->loss.kind != SCS_LOSS_QUADFORM) {
+    GramPlan& pl = p->plan;
+    pl.nt = (int)((m + kGT - 1) / kGT);
+    pl.ntiles = pl.nt * (pl.nt + 1) / 2;
+    pl.kt = p->ldd / kGBK;
+    p->ldp = (int)round_up(m, 2);
+    // pick the K split that best fills whole waves of num_sms CTAs; each unit keeps >= 8 stages of work and
+    // the partial buffers stay under 4 GiB
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double per_split = (double)m * p->ldp * 8.0;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int s = 1; s <= 32; ++s) {
+      if (s > 1 && pl.kt / s < 8) break;
+      if (s > 1 && per_split * s > std::min<double>(4.0 * (1ull << 30), 0.25 * (double)free_b)) break;
+      const double units = (double)pl.ntiles * s;
+      const double waves = std::ceil(units / c->num_sms);
+      const double eff = units / (waves * c->num_sms);
+      if (eff > best_eff + 0.004) {
+        best_eff = eff;
+        best = s;
+      }
+    }
+    pl.splits = best;
+    pl.units = (int64_t)pl.ntiles * pl.splits;
+    SCS_TRY(dalloc(&p->d_partial, (size_t)pl.splits * m * p->ldp));
+    if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[2] = {(cuuint64_t)p->ldd, (cuuint64_t)m};
+    cuuint64_t gstride[1] = {(cuuint64_t)p->ldd * 8};
+    cuuint32_t box[2] = {(cuuint32_t)kGBK, (cuuint32_t)kGT};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(&p->amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->dA, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    CU_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemBytes));
+  }
+  p->gram_ready = true;
+  return SCS_OK;
+}
+
+// G = A' diag(w) A (all-reduced, both triangles) into d_G, using the weights currently in d_w
+static int run_gram(scs_problem* p, XRef x) {
+  scs_ctx* c = p->ctx;
+  SCS_TRY(gram_setup(p));
+  const int m = (int)p->m;
+  if (p->loss.kind == SCS_LOSS_QUADFORM) {
+    StageTimer t(c, ST_GRAM);
+    LAUNCH(c, k_quadform_hess, dim3((m + 255) / 256, m), 256, 0, p->dA, p->ldd, m, p->d_G);
+    return SCS_OK;
+  }
+  {
+    StageTimer t(c, ST_GRAM);
+    const int grid = (int)std::min<int64_t>(c->num_sms, p->plan.units);
+    LAUNCH(c, k_gram, grid, kGThreads, kGSmemBytes, p->amap, p->dw, m, p->ldp, p->plan, p->d_partial);
+    const int t32 = (m + 31) / 32;
+    LAUNCH(c, k_gram_finalize, t32 * (t32 + 1) / 2, 256, 0, p->d_partial, p->plan.splits, m, p->ldp, p->d_G);
+  }
+  SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
+  return SCS_OK;
+}
+
+// Solve M d = b on the device.  M (ld = m) is destroyed; Msave receives a copy first (for the LU fallback).
+// b is destroyed; result in dsol.  tmp: m doubles.
+static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
+                     double* dsol, int m, int* used_fallback) {
+  StageTimer t(c, ST_SOLVE);
+  CU_TRY(cudaMemcpyAsync(Msave, M, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(tmp, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
+  const int nblk = (m + kNB - 1) / kNB;
+  for (int k = 0; k < nblk; ++k) {
+    const int k0 = k * kNB;
+    const int nb = std::min(kNB, m - k0);
+    LAUNCH(c, k_potf2, 1, 256, 0, M, (int64_t)m, m, k0, Linv + (size_t)k * kNB * kNB, d_info);
+    const int rem = m - k0 - nb;
+    if (rem > 0) {
+      const int rb = (rem + kNB - 1) / kNB;
+      LAUNCH(c, k_trsm_panel, rb, 256, 0, M, (int64_t)m, m, k0, Linv + (size_t)k * kNB * kNB);
+      LAUNCH(c, k_syrk_update, rb * (rb + 1) / 2, 256, 0, M, (int64_t)m, m, k0);
+    }
+  }
+  int info = 0;
+  CU_TRY(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  if (info == 0) {
+    // L y = b (y -> dsol as scratch), then L' d = y (d -> dsol)
+    for (int k = 0; k < nblk; ++k) {
+      const int k0 = k * kNB, nb = std::min(kNB, m - k0);
+      const int rem = m - k0 - nb;
+      LAUNCH(c, k_fwd_step, std::max(1, (rem + 255) / 256), 256, 0, M, (int64_t)m, m, k0,
+             Linv + (size_t)k * kNB * kNB, b, tmp);
+    }
+    // tmp now holds y
+    for (int k = nblk - 1; k >= 0; --k) {
+      const int k0 = k * kNB;
+      LAUNCH(c, k_bwd_step, std::max(1, (k0 + 255) / 256), 256, 0, M, (int64_t)m, m, k0,
+             Linv + (size_t)k * kNB * kNB, tmp, dsol);
+    }
+    *used_fallback = 0;
+    return SCS_OK;
+  }
+  // not positive definite: partial-pivoting LU on the saved copy (symmetrised), still on the device
+  *used_fallback = 1;
+  LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, Msave, (int64_t)m, m);
+  // restore b (the Cholesky path has not touched b yet, but keep the contract explicit)
+  CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
+  for (int k = 0; k < m; ++k) {
+    LAUNCH(c, k_lu_pivot, 1, kVecThreads, 0, Msave, (int64_t)m, m, k, b, d_info);
+    const int rem = m - k - 1;
+    if (rem > 0) LAUNCH(c, k_lu_update, dim3((rem + 255) / 256, (rem + 15) / 16), 256, 0, Msave, (int64_t)m, m, k, b);
+  }
+  LAUNCH(c, k_lu_backsolve, 1, kVecThreads, 0, Msave, (int64_t)m, m, b, dsol);
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported: misc
+// ------------------------------------------------------------------------------------------------
+extern "C" int scs_version(void) { return SCS_B200_VERSION; }
+extern "C" const char* scs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int scs_comm_unique_id(void* id128) {
+  if (!id128) return fail(SCS_INVALID_ARG, "id128 is NULL");
+  const char* why = "";
+  if (!g_nccl.load(&why)) return fail(SCS_NCCL_ERROR, why);
+  NcclUniqueId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(SCS_NCCL_ERROR, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+  memcpy(id128, &id, 128);
+  return SCS_OK;
+}
+
+extern "C" int scs_ctx_create(int device, int rank, int world, const void* id128, scs_ctx** out) {
+  if (!out) return fail(SCS_INVALID_ARG, "out is NULL");
+  if (world < 1 || rank < 0 || rank >= world) return fail(SCS_INVALID_ARG, "bad rank/world");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SCS_CUDA_ERROR, std::string("no CUDA device available (this library has no CPU path): ") +
+                                    cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(SCS_INVALID_ARG, "device index out of range");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SCS_UNSUPPORTED, "scs_b200 kernels are built for sm_100a only; found compute capability " +
+                                     std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  scs_ctx* c = new scs_ctx();
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  c->num_sms = prop.multiProcessorCount;
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    c->encode = (EncodeTiledFn)fn;
+  if (world > 1) {
+    if (!id128) {
+      delete c;
+      return fail(SCS_INVALID_ARG, "world > 1 needs a unique id");
+    }
+    const char* why = "";
+    if (!g_nccl.load(&why)) {
+      delete c;
+      return fail(SCS_NCCL_ERROR, why);
+    }
+    NcclUniqueId id;
+    memcpy(&id, id128, 128);
+    int r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) {
+      delete c;
+      return fail(SCS_NCCL_ERROR, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    }
+  }
+  *out = c;
+  return SCS_OK;
+}
+
+extern "C" int scs_ctx_destroy(scs_ctx* c) {
+  if (!c) return SCS_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  harvest_timers(c);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return SCS_OK;
+}
+extern "C" int scs_ctx_sync(scs_ctx* c) {
+  if (!c) return fail(SCS_INVALID_ARG, "ctx is NULL");
+  return ctx_sync(c);
+}
+extern "C" int scs_ctx_stream(scs_ctx* c, uint64_t* s) {
+  if (!c || !s) return fail(SCS_INVALID_ARG, "NULL argument");
+  *s = (uint64_t)(uintptr_t)c->stream;
+  return SCS_OK;
+}
+extern "C" int scs_get_counters(scs_ctx* c, int64_t* launches, int reset) {
+  if (!c) return fail(SCS_INVALID_ARG, "ctx is NULL");
+  if (launches) *launches = c->launches;
+  if (reset) c->launches = 0;
+  return SCS_OK;
+}
+extern "C" int scs_set_profiling(scs_ctx* c, int enable) {
+  if (!c) return fail(SCS_INVALID_ARG, "ctx is NULL");
+  c->profiling = enable != 0;
+  return SCS_OK;
+}
+extern "C" int scs_get_stage_ms(scs_ctx* c, double* ms8, int64_t* calls8, int reset) {
+  if (!c) return fail(SCS_INVALID_ARG, "ctx is NULL");
+  SCS_TRY(ctx_sync(c));
+  for (int i = 0; i < ST_N; ++i) {
+    if (ms8) ms8[i] = c->stage_ms[i];
+    if (calls8) calls8[i] = c->stage_calls[i];
+    if (reset) {
+      c->stage_ms[i] = 0;
+      c->stage_calls[i] = 0;
+    }
+  }
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported: problem lifetime
+// ------------------------------------------------------------------------------------------------
+static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind, double loss_param, int label_mode,
+                         scs_problem** out) {
+  if (!ctx || !out) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (n_local < 1 || m < 1) return fail(SCS_INVALID_ARG, "n_local and m must be positive");
+  if (m > 2000000000LL) return fail(SCS_INVALID_ARG, "m too large");
+  if (loss_kind < 0 || loss_kind > 2) return fail(SCS_INVALID_ARG, "unknown loss_kind");
+  if (label_mode < 0 || label_mode > 1) return fail(SCS_INVALID_ARG, "unknown label_mode");
+  if (loss_kind == SCS_LOSS_QUADFORM) {
+    if (n_local != m) return fail(SCS_INVALID_ARG, "quadform loss needs a square A");
+    if (ctx->world != 1) return fail(SCS_UNSUPPORTED, "quadform loss is single-GPU only");
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  scs_problem* p = new scs_problem();
+  p->ctx = ctx;
+  p->n = n_local;
+  p->m = m;
+  p->ldd = round_up(n_local, 16);
+  p->mp = round_up(m, 16);
+  p->loss.kind = loss_kind;
+  p->loss.label_mode = label_mode;
+  p->loss.weight_kind = 0;
+  p->loss.p = loss_param;
+  *out = p;
+  SCS_TRY(dalloc(&p->dA, (size_t)p->ldd * m));
+  SCS_TRY(dalloc(&p->dy, p->ldd));
+  SCS_TRY(dalloc(&p->dz, p->ldd));
+  SCS_TRY(dalloc(&p->dr, p->ldd));
+  SCS_TRY(dalloc(&p->dw, p->ldd));
+  for (int i = 0; i < 3; ++i) SCS_TRY(dalloc(&p->vx[i], p->mp));
+  SCS_TRY(dalloc(&p->d_gl, p->mp + 16));
+  double** vecs[] = {&p->d_gr,    &p->d_hr,     &p->d_rhs,   &p->d_sol, &p->d_d,  &p->d_dx, &p->d_delta,
+                     &p->d_gq,    &p->d_gqprev, &p->d_gamma, &p->d_q,   &p->d_t1, &p->d_t2, &p->d_xstar,
+                     &p->d_trial, &p->d_gnewton};
+  for (auto v : vecs) SCS_TRY(dalloc(v, p->mp));
+  SCS_TRY(dalloc(&p->d_scal, SC_COUNT));
+  CU_TRY(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 8) * sizeof(double)));
+  p->fwd_blocks = (n_local + kFwdRows - 1) / kFwdRows;
+  p->adj_blocks = (p->ldd + 64 * 8 - 1) / (64 * 8);
+  SCS_TRY(dalloc(&p->d_losspart, p->fwd_blocks));
+  SCS_TRY(dalloc(&p->d_adjpart, (size_t)p->adj_blocks * m));
+  return SCS_OK;
+}
+
+extern "C" int scs_problem_destroy(scs_problem* p) {
+  if (!p) return SCS_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  void* bufs[] = {p->dA,      p->dy,      p->dz,     p->dr,      p->dw,       p->vx[0],   p->vx[1],    p->vx[2],
+                  p->d_gl,    p->d_gr,    p->d_hr,   p->d_rhs,   p->d_sol,    p->d_d,     p->d_dx,     p->d_delta,
+                  p->d_gq,    p->d_gqprev, p->d_gamma, p->d_q,   p->d_t1,     p->d_t2,    p->d_xstar,  p->d_trial,
+                  p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
+                  p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
+                  p->d_cdiag, p->d_ind,   p->d_perm};
+  for (void* b : bufs) dfree(b);
+  if (p->h_scal) cudaFreeHost(p->h_scal);
+  delete p;
+  return SCS_OK;
+}
+
+extern "C" int scs_problem_create(scs_ctx* ctx, const double* A, int64_t n_local, int64_t m, int64_t lda,
+                                  const double* y, int loss_kind, double loss_param, int label_mode,
+                                  scs_problem** out) {
+  if (!A || !y) return fail(SCS_INVALID_ARG, "A or y is NULL");
+  if (lda < n_local) return fail(SCS_INVALID_ARG, "lda < n_local");
+  int s = problem_alloc(ctx, n_local, m, loss_kind, loss_param, label_mode, out);
+  if (s != SCS_OK) {
+    if (out && *out) {
+      scs_problem_destroy(*out);
+      *out = nullptr;
+    }
+    return s;
+  }
+  scs_problem* p = *out;
+  cudaError_t e = cudaMemcpy2DAsync(p->dA, p->ldd * sizeof(double), A, lda * sizeof(double),
+                                    n_local * sizeof(double), m, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(p->dy, y, n_local * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    scs_problem_destroy(p);
+    *out = nullptr;
+    return fail(SCS_CUDA_ERROR, std::string("upload of A/y failed: ") + cudaGetErrorString(e));
+  }
+  return SCS_OK;
+}
+
+extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64_t row0, int64_t n_local, int64_t m,
+                                            int loss_kind, double loss_param, int label_mode, uint64_t seed,
+                                            double density, scs_problem** out) {
+  if (loss_kind == SCS_LOSS_QUADFORM) return fail(SCS_INVALID_ARG, "no synthetic generator for quadform");
+  if (row0 < 0 || row0 + n_local > n_total) return fail(SCS_INVALID_ARG, "row range outside n_total");
+  int s = problem_alloc(ctx, n_local, m, loss_kind, loss_param, label_mode, out);
+  if (s != SCS_OK) {
+    if (out && *out) {
+      scs_problem_destroy(*out);
+      *out = nullptr;
+    }
+    return s;
+  }
+  scs_problem* p = *out;
+  const unsigned gy = (unsigned)std::min<int64_t>(m, 1024);
+  LAUNCH(ctx, k_synth_A, dim3((unsigned)((n_local + 255) / 256), gy), 256, 0, p->dA, p->ldd, n_local, (int)m, row0,
+         n_total, seed, density, 1.0 / std::sqrt((double)m));
+  LAUNCH(ctx, k_synth_xtrue, (unsigned)((m + 255) / 256), 256, 0, p->d_t1, (int)m, seed + 1, 0.05, 3.0);
+  // z = A x_true (a forward pass with the z-only loss kind), then labels / targets
+  LossParams lp = p->loss;
+  lp.kind = 2;
+  LAUNCH(ctx, k_forward<8>, (unsigned)p->fwd_blocks, kFwdThreads, 0, p->dA, p->ldd, p->n, (int)m, p->d_t1, p->dy, lp,
+         p->dz, (double*)nullptr, (double*)nullptr, p->d_losspart);
+  LAUNCH(ctx, k_synth_y, (unsigned)((n_local + 255) / 256), 256, 0, p->dy, p->dz, n_local, row0, seed + 2,
+         loss_kind == SCS_LOSS_LOGISTIC ? 0 : 1, 0.1);
+  CU_TRY(cudaMemsetAsync(p->dz, 0, p->ldd * sizeof(double), ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return SCS_OK;
+}
+
+extern "C" int scs_problem_read_rows(scs_problem* p, int64_t row0, int64_t nrows, double* A_out, double* y_out) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > p->n) return fail(SCS_INVALID_ARG, "row range outside the shard");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+  if (A_out && nrows > 0)
+    CU_TRY(cudaMemcpy2D(A_out, nrows * sizeof(double), p->dA + row0, p->ldd * sizeof(double),
+                        nrows * sizeof(double), p->m, cudaMemcpyDeviceToHost));
+  if (y_out && nrows > 0) CU_TRY(cudaMemcpy(y_out, p->dy + row0, nrows * sizeof(double), cudaMemcpyDeviceToHost));
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported: configuration
+// ------------------------------------------------------------------------------------------------
+static int upload_bounds(double** dst, const double* src, int64_t n, bool sanity) {
+  std::vector<double> h(src, src + n);
+  if (sanity)  // bounds_sanity_check: ±Inf -> ±1e32 (prox-reg-utils.jl:156-157)
+    for (auto& v : h) {
+      if (v == -std::numeric_limits<double>::infinity()) v = -1e32;
+      if (v == std::numeric_limits<double>::infinity()) v = 1e32;
+    }
+  dfree(*dst);
+  *dst = nullptr;
+  CU_TRY(cudaMalloc((void**)dst, n * sizeof(double)));
+  CU_TRY(cudaMemcpy(*dst, h.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  return SCS_OK;
+}
+
+extern "C" int scs_set_regularizer(scs_problem* p, int reg_kind, double lam1, double lam2, const int64_t* ind3xG,
+                                   int64_t ngroups, const int64_t* perm, const double* lb, int64_t nlb,
+                                   const double* ub, int64_t nub) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (reg_kind < 0 || reg_kind > 3) return fail(SCS_INVALID_ARG, "reg_name not valid.");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  RegDesc rd{};
+  rd.kind = reg_kind;
+  rd.lam1 = lam1;
+  rd.lam2 = lam2;
+  if (reg_kind == SCS_REG_INDBOX) {
+    if (!lb || !ub) return fail(SCS_INVALID_ARG, "indbox needs C_set bounds");
+    if (!((nlb == 1 || nlb == p->m) && (nub == 1 || nub == p->m)))
+      return fail(SCS_INVALID_ARG, "Lengths of the bounds do not match that of the variable.");
+    SCS_TRY(upload_bounds(&p->d_rlb, lb, nlb, false));
+    SCS_TRY(upload_bounds(&p->d_rub, ub, nub, false));
+    rd.lb = p->d_rlb;
+    rd.ub = p->d_rub;
+    rd.nlb = (int)nlb;
+    rd.nub = (int)nub;
+  }
+  if (reg_kind == SCS_REG_GL) {
+    if (!ind3xG || ngroups < 1) return fail(SCS_INVALID_ARG, "gl needs the group index table (model.P)");
+    // groups must tile 1..m contiguously (then Cmat == diag(weights), prox-reg-utils.jl:121-142)
+    std::vector<double> cd(p->m, 0.0);
+    int64_t expect = 1;
+    for (int64_t g = 0; g < ngroups; ++g) {
+      const int64_t gs = ind3xG[3 * g], ge = ind3xG[3 * g + 1], gw = ind3xG[3 * g + 2];
+      if (gs != expect || ge < gs || ge > p->m)
+        return fail(SCS_UNSUPPORTED, "gl groups must be contiguous, non-overlapping and cover 1..m in order");
+      for (int64_t k = gs; k <= ge; ++k) cd[k - 1] = (double)gw;
+      expect = ge + 1;
+    }
+    if (expect != p->m + 1) return fail(SCS_UNSUPPORTED, "gl groups must cover all m variables");
+    dfree(p->d_ind);
+    p->d_ind = nullptr;
+    CU_TRY(cudaMalloc((void**)&p->d_ind, 3 * ngroups * sizeof(int64_t)));
+    CU_TRY(cudaMemcpy(p->d_ind, ind3xG, 3 * ngroups * sizeof(int64_t), cudaMemcpyHostToDevice));
+    dfree(p->d_perm);
+    p->d_perm = nullptr;
+    if (perm) {
+      for (int64_t k = 0; k < p->m; ++k)
+        if (perm[k] < 1 || perm[k] > p->m) return fail(SCS_INVALID_ARG, "perm entries must be in 1..m");
+      CU_TRY(cudaMalloc((void**)&p->d_perm, p->m * sizeof(int64_t)));
+      CU_TRY(cudaMemcpy(p->d_perm, perm, p->m * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    dfree(p->d_cdiag);
+    p->d_cdiag = nullptr;
+    CU_TRY(cudaMalloc((void**)&p->d_cdiag, p->m * sizeof(double)));
+    CU_TRY(cudaMemcpy(p->d_cdiag, cd.data(), p->m * sizeof(double), cudaMemcpyHostToDevice));
+    rd.ind = p->d_ind;
+    rd.ngroups = (int)ngroups;
+    rd.perm = p->d_perm;
+    p->sm.cdiag = p->d_cdiag;
+  }
+  p->reg = rd;
+  p->has_reg = true;
+  return SCS_OK;
+}
+
+extern "C" int scs_set_smoother(scs_problem* p, int kind, double mu, const double* lb, int64_t nlb, const double* ub,
+                                int64_t nub) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (kind < 0 || kind > 6) return fail(SCS_INVALID_ARG, "unknown smoother kind");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  SmoothDesc sd{};
+  sd.kind = kind;
+  sd.mu = mu;
+  sd.cdiag = p->d_cdiag;
+  const bool box = kind == SCS_SMOOTH_PHUBER_INDBOX || kind == SCS_SMOOTH_EXP_INDBOX || kind == SCS_SMOOTH_LOGEXP_INDBOX;
+  if (box) {
+    if (!lb || !ub) return fail(SCS_INVALID_ARG, "IndBox smoothers need lb and ub");
+    if (!((nlb == 1 && nub == 1) || (nlb == p->m && nub == p->m)))
+      return fail(SCS_INVALID_ARG, "Lengths of the bounds do not match that of the variable.");
+    SCS_TRY(upload_bounds(&p->d_slb, lb, nlb, true));
+    SCS_TRY(upload_bounds(&p->d_sub, ub, nub, true));
+    sd.lb = p->d_slb;
+    sd.ub = p->d_sub;
+    sd.nlb = (int)nlb;
+    sd.nub = (int)nub;
+  }
+  switch (kind) {  // Mh, ν constants: phuber-smooth.jl:3-4, exponential-smooth.jl:25-26, log-exp-smooth.jl:25-26,
+                   // ostrovskii-bach-smooth.jl:3-4
+    case SCS_SMOOTH_PHUBER_L1L2:
+    case SCS_SMOOTH_PHUBER_INDBOX:
+    case SCS_SMOOTH_PHUBER_GL:
+      p->Mh = 2.0;
+      p->nu = 2.6;
+      break;
+    case SCS_SMOOTH_EXP_INDBOX:
+    case SCS_SMOOTH_LOGEXP_INDBOX:
+      p->Mh = 1.0;
+      p->nu = 2.0;
+      break;
+    default:
+      p->Mh = 2.0 * std::sqrt(2.0);
+      p->nu = 3.0;
+  }
+  p->sm = sd;
+  p->has_sm = true;
+  return SCS_OK;
+}
+
+extern "C" int scs_set_method(scs_problem* p, int method_kind, int ss_type, int use_prox, int lbfgs_m) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (method_kind < 0 || method_kind > 2) return fail(SCS_INVALID_ARG, "unknown method kind");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  if (method_kind == SCS_METHOD_GGN && p->loss.kind == SCS_LOSS_QUADFORM)
+    return fail(SCS_UNSUPPORTED, "ProxGGNSCORE needs a model output function (out_fn); the quadform loss has none");
+  p->method = method_kind;
+  p->ss_type = ss_type;  // validated in scs_step, like the reference (error raised inside step!)
+  p->use_prox = use_prox != 0;
+  if (method_kind == SCS_METHOD_LQN) {
+    if (lbfgs_m < 1 || lbfgs_m > 64) return fail(SCS_INVALID_ARG, "L-BFGS memory must be in 1..64");
+    if (lbfgs_m != p->lbfgs_cap) {
+      dfree(p->d_S);
+      dfree(p->d_Y);
+      dfree(p->d_state);
+      p->d_S = p->d_Y = nullptr;
+      p->d_state = nullptr;
+      SCS_TRY(dalloc(&p->d_S, (size_t)lbfgs_m * p->m));
+      SCS_TRY(dalloc(&p->d_Y, (size_t)lbfgs_m * p->m));
+      CU_TRY(cudaMalloc((void**)&p->d_state, 2 * sizeof(int64_t)));
+      CU_TRY(cudaMemset(p->d_state, 0, 2 * sizeof(int64_t)));
+      p->lbfgs_cap = lbfgs_m;
+    }
+    p->lbfgs_m = lbfgs_m;
+  }
+  p->has_method = true;
+  return SCS_OK;
+}
+
+extern "C" int scs_set_L(scs_problem* p, int has_L, double L) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  p->has_L = has_L != 0;
+  p->L = L;
+  return SCS_OK;
+}
+
+extern "C" int scs_method_init(scs_problem* p) {  // init!(method, x): prox-L-BFGS-SCORE.jl:31-36
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (!p->has_method) return fail(SCS_STATE_ERROR, "scs_set_method has not been called");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  if (p->method == SCS_METHOD_LQN) {
+    CU_TRY(cudaMemsetAsync(p->d_state, 0, 2 * sizeof(int64_t), p->ctx->stream));
+    const double one = 1.0;
+    CU_TRY(cudaMemcpyAsync(p->d_scal + SC_H0, &one, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+  }
+  p->gq_id = 0;
+  p->gqprev_id = 0;
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x interning: host vectors get ids so that passes are reused when the same iterate comes back
+// ------------------------------------------------------------------------------------------------
+static int intern_x(scs_problem* p, const double* hx, double* dbuf, XRef* out) {
+  const size_t bytes = p->m * sizeof(double);
+  uint64_t id = 0;
+  for (auto& s : p->shadow)
+    if (s.id != 0 && s.x.size() == (size_t)p->m && memcmp(s.x.data(), hx, bytes) == 0) {
+      id = s.id;
+      break;
+    }
+  if (id == 0) {
+    auto& s = p->shadow[p->shadow_next];
+    p->shadow_next = (p->shadow_next + 1) % 4;
+    s.x.assign(hx, hx + p->m);
+    s.id = id = p->next_id++;
+  }
+  CU_TRY(cudaMemcpyAsync(dbuf, hx, bytes, cudaMemcpyHostToDevice, p->ctx->stream));
+  out->d = dbuf;
+  out->id = id;
+  return SCS_OK;
+}
+static void remember_x(scs_problem* p, const double* hx, uint64_t id) {
+  auto& s = p->shadow[p->shadow_next];
+  p->shadow_next = (p->shadow_next + 1) % 4;
+  s.x.assign(hx, hx + p->m);
+  s.id = id;
+}
+
+static int get_Mg(const scs_problem* p, double* Mg) {  // smoothing.jl:12-26
+  if (p->Mh < 0) return fail(SCS_INVALID_ARG, "Mh must be nonnegative.");
+  if (!(p->sm.mu > 0)) return fail(SCS_INVALID_ARG, "μ must be positive.");
+  if (p->nu > 0 && p->nu <= 3)
+    *Mg = std::pow((double)p->m, (3 - p->nu) / 2) * std::pow(p->sm.mu, p->nu / 2 - 2) * p->Mh;
+  else if (p->nu > 3)
+    *Mg = std::pow(p->sm.mu, 4 - 3 * p->nu / 2) * p->Mh;
+  else
+    return fail(SCS_INVALID_ARG, "ν must be positive.");
+  return SCS_OK;
+}
+
+static int check_ready(const scs_problem* p) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (!p->has_reg) return fail(SCS_STATE_ERROR, "scs_set_regularizer has not been called");
+  return SCS_OK;
+}
+
+// objective pieces at x: loss sum (all-reduced) in d_gl[m], reg value in d_scal[SC_REGX]
+static int objective_device(scs_problem* p, XRef x) {
+  const int wk = p->method == SCS_METHOD_GGN ? SCS_WEIGHTS_GGN : SCS_WEIGHTS_NEWTON;
+  // reuse whatever forward pass is cached for this x: the loss value does not depend on the weight kind
+  if (p->fwd_id == x.id)
+    SCS_TRY(ensure_loss(p, x, p->fwd_wk));
+  else
+    SCS_TRY(ensure_loss(p, x, wk));
+  StageTimer t(p->ctx, ST_VEC);
+  LAUNCH(p->ctx, k_reg, 1, kVecThreads, 0, p->reg, x.d, (int)p->m, p->d_scal + SC_REGX);
+  return SCS_OK;
+}
+
+extern "C" int scs_objective(scs_problem* p, const double* x, double* fval, double* reg) {
+  SCS_TRY(check_ready(p));
+  if (!x) return fail(SCS_INVALID_ARG, "x is NULL");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  XRef xr;
+  SCS_TRY(intern_x(p, x, p->vx[0], &xr));
+  SCS_TRY(objective_device(p, xr));
+  CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_gl + p->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->h_scal + 1, p->d_scal + SC_REGX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  if (fval) *fval = fval_from_sum(p, p->h_scal[0]);
+  if (reg) *reg = p->h_scal[1];
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step
+// ------------------------------------------------------------------------------------------------
+// ∇q(v) = grad_f(v) + λ·hμ.grad(v) into dout (invalidates the forward cache unless v is the cached x)
+static int compute_gq(scs_problem* p, XRef v, double lam, double* dout) {
+  SCS_TRY(ensure_grad(p, v, SCS_WEIGHTS_NEWTON));
+  StageTimer t(p->ctx, ST_VEC);
+  LAUNCH(p->ctx, k_pre, 1, kVecThreads, 0, p->sm, lam, v.d, p->d_gl, (int)p->m, p->d_t1, p->d_t2, dout, p->d_scal + SC_GG);
+  return SCS_OK;
+}
+
+// Armijo backtracking of utils.jl:27-35 with f = nonsmooth objective, grad = smoothed ∇q.  f(x) and <∇q,d> are
+// evaluated once (the reference recomputes the same values every trial).
+static int linesearch_device(scs_problem* p, XRef x, const double* d_dir, double dsign, const double* d_gqx,
+                             double* ss_out) {
+  scs_ctx* c = p->ctx;
+  SCS_TRY(ensure_loss(p, x, p->fwd_id == x.id ? p->fwd_wk : SCS_WEIGHTS_NEWTON));
+  LAUNCH(c, k_reg, 1, kVecThreads, 0, p->reg, x.d, (int)p->m, p->d_scal + SC_REGX);
+  LAUNCH(c, k_dot, 1, kVecThreads, 0, d_gqx, d_dir, (int)p->m, p->d_scal, (int)SC_GD);
+  CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_gl + p->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->h_scal + 1, p->d_scal + SC_REGX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->h_scal + 2, p->d_scal + SC_GD, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  const double fx = fval_from_sum(p, p->h_scal[0]) + p->h_scal[1];
+  const double gd = dsign * p->h_scal[2];
+  double alpha = 1.0;
+  for (int it = 0; it < 4000; ++it) {
+    LAUNCH(c, k_axpy_out, (unsigned)((p->m + 255) / 256), 256, 0, x.d, dsign * alpha, d_dir, (int)p->m, p->d_trial);
+    XRef tr{p->d_trial, p->next_id++};
+    SCS_TRY(ensure_loss(p, tr, SCS_WEIGHTS_NEWTON));
+    LAUNCH(c, k_reg, 1, kVecThreads, 0, p->reg, p->d_trial, (int)p->m, p->d_scal + SC_REGX);
+    CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_gl + p->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(p->h_scal + 1, p->d_scal + SC_REGX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const double ft = fval_from_sum(p, p->h_scal[0]) + p->h_scal[1];
+    if (!(ft > fx + 1e-4 * alpha * gd)) break;
+    alpha = 0.5 * alpha;
+  }
+  *ss_out = alpha;
+  return SCS_OK;
+}
+
+// One step! on device vectors.  x, x_prev: inputs; xnew: output buffer.  Scalars land in h_scal after the sync
+// the caller performs.
+static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double* xnew, uint64_t xnew_id,
+                       const double* d_xstar) {
+  scs_ctx* c = p->ctx;
+  const int m = (int)p->m;
+  const double lam = p->reg.lam1;  // model.λ or model.λ[1]
+  double Mg = 0;
+  SCS_TRY(get_Mg(p, &Mg));
+  double ss = 0.5;
+  const bool type1 = p->ss_type == 1;
+  if (type1) ss = p->has_L ? std::min(1.0 / p->L, 1.0) : 0.5;
+
+  if (p->method == SCS_METHOD_N || p->method == SCS_METHOD_GGN) {
+    const bool ggn = p->method == SCS_METHOD_GGN;
+    const int wk = ggn ? SCS_WEIGHTS_GGN : SCS_WEIGHTS_NEWTON;
+    if (ggn && (int64_t)p->n * c->world + 1 <= p->m && c->world == 1)
+      return fail(SCS_UNSUPPORTED,
+                  "ProxGGNSCORE underdetermined branch (n+1 <= m, prox-GGN-SCORE.jl:124-127) is not implemented on the GPU");
+    if (!type1 && p->ss_type != 2 && p->ss_type != 3) return fail(SCS_INVALID_ARG, "Please, choose ss_type in [1, 2, 3].");
+    if (p->ss_type == 2) {
+      // prox-N-SCORE.jl:81-83 / prox-GGN-SCORE.jl:78-80 reference an undefined ∇f: the reference throws after iter 1
+      if (iter == 1)
+        ss = 1.0;
+      else
+        return fail(SCS_UNSUPPORTED,
+                    "ss_type=2 is broken in the reference for ProxNSCORE/ProxGGNSCORE (UndefVarError: ∇f); rejected");
+    }
+    SCS_TRY(ensure_grad(p, x, wk));
+    SCS_TRY(run_gram(p, x));
+    {
+      StageTimer t(c, ST_VEC);
+      LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_rhs, p->d_scal);
+      LAUNCH(c, k_add_diag, (m + 255) / 256, 256, 0, p->d_G, m, lam, p->d_hr);
+      CU_TRY(cudaMemcpyAsync(p->d_q, p->d_rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    SCS_TRY(run_solve(c, p->d_G, p->d_Gsave, p->d_Linv, p->d_info, p->d_q, p->d_t1, p->d_sol, m,
+                      &p->last_used_fallback));
+    if (p->ss_type == 3) {
+      const double* gqx = p->d_rhs;  // N: ∇q = grad_f + λgr
+      if (ggn) {                     // GGN's rhs is J'res + λgr; the line search wants the gradient of f(A,y,x)
+        SCS_TRY(compute_gq(p, x, lam, p->d_gnewton));
+        gqx = p->d_gnewton;
+      }
+      SCS_TRY(linesearch_device(p, x, p->d_sol, -1.0, gqx, &ss));
+    }
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_tail, 1, kVecThreads, 0, p->reg, p->use_prox, ss, Mg, -1.0, x.d, p->d_sol, p->d_hr, d_xstar, m, xnew,
+           p->d_dx, (double*)nullptr, p->d_scal);
+    return SCS_OK;
+  }
+
+  // ---- ProxLQNSCORE ----
+  if (!(type1 || p->ss_type == 2 || p->ss_type == 3 || !p->has_L))
+    return fail(SCS_INVALID_ARG, "Please, choose ss_type in [1, 2, 3].");
+  if (p->gq_id == x.id) {
+    StageTimer t(c, ST_VEC);  // ∇q carried over from the previous step; only gr, Hr, η are needed
+    LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, (const double*)nullptr, m, p->d_gr, p->d_hr,
+           (double*)nullptr, p->d_scal);
+  } else {
+    SCS_TRY(ensure_grad(p, x, SCS_WEIGHTS_NEWTON));
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_gq, p->d_scal);
+    p->gq_id = x.id;
+  }
+  {
+    StageTimer t(c, ST_VEC);
+    LbfgsMem mem{p->d_S, p->d_Y, p->d_state, p->lbfgs_cap};
+    LAUNCH(c, k_lbfgs_dir, 1, kVecThreads, 0, mem, iter, p->d_gq, m, p->d_q, p->d_d, p->d_scal);
+  }
+  if (!type1) {
+    if (p->ss_type == 2 || !p->has_L) {  // prox-L-BFGS-SCORE.jl:112-119 (ss_type 3 without L lands here too)
+      if (iter == 1) {
+        ss = 1.0;
+      } else {
+        if (p->gqprev_id != xprev.id) {
+          // ∇q(x_prev) is not the one carried over: recompute it (keeps the current ∇q and forward cache intact
+          // only by id, so restore them afterwards)
+          SCS_TRY(compute_gq(p, xprev, lam, p->d_gqprev));
+          p->gqprev_id = xprev.id;
+        }
+        LAUNCH(c, k_bb, 1, kVecThreads, 0, x.d, xprev.d, p->d_gq, p->d_gqprev, m, p->d_scal);
+        CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal + SC_GG, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        ss = p->h_scal[0] / p->h_scal[1];  // (γ·γ)/(δ'γ), used *as* the step size
+        // k_pre's η² lives in SC_ETASQ and is untouched by compute_gq (it wrote to SC_GG..)
+      }
+    } else {
+      SCS_TRY(linesearch_device(p, x, p->d_d, 1.0, p->d_gq, &ss));
+    }
+  }
+  {
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_tail, 1, kVecThreads, 0, p->reg, p->use_prox, ss, Mg, 1.0, x.d, p->d_d, p->d_hr, d_xstar, m, xnew,
+           p->d_dx, p->d_delta, p->d_scal);
+  }
+  // second gradient at x⁺ (prox-L-BFGS-SCORE.jl:148-150); it is next iteration's ∇q, and its loss value is next
+  // epoch's objective, so neither is recomputed
+  XRef xn{xnew, xnew_id};
+  SCS_TRY(ensure_grad(p, xn, SCS_WEIGHTS_NEWTON));
+  {
+    StageTimer t(c, ST_VEC);
+    CU_TRY(cudaMemcpyAsync(p->d_gqprev, p->d_gq, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    p->gqprev_id = x.id;
+    LbfgsMem mem{p->d_S, p->d_Y, p->d_state, p->lbfgs_cap};
+    LAUNCH(c, k_lbfgs_update, 1, kVecThreads, 0, p->sm, lam, mem, xnew, p->d_gl, p->d_delta, m, p->d_gq, p->d_gamma,
+           p->d_t1, p->d_t2, p->d_scal);
+    p->gq_id = xnew_id;
+  }
+  return SCS_OK;
+}
+
+extern "C" int scs_step(scs_problem* p, const double* x, const double* x_prev, int64_t iter, double* x_new, double* dx,
+                        double* pri_res_norm) {
+  SCS_TRY(check_ready(p));
+  if (!p->has_sm) return fail(SCS_STATE_ERROR, "scs_set_smoother has not been called");
+  if (!p->has_method) return fail(SCS_STATE_ERROR, "scs_set_method has not been called");
+  if (!x || !x_new) return fail(SCS_INVALID_ARG, "x or x_new is NULL");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  XRef xr, xp;
+  SCS_TRY(intern_x(p, x, p->vx[0], &xr));
+  if (x_prev)
+    SCS_TRY(intern_x(p, x_prev, p->vx[1], &xp));
+  else
+    xp = xr;
+  const uint64_t nid = p->next_id++;
+  SCS_TRY(step_device(p, xr, xp, iter, p->vx[2], nid, nullptr));
+  CU_TRY(cudaMemcpyAsync(x_new, p->vx[2], p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (dx) CU_TRY(cudaMemcpyAsync(dx, p->d_dx, p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  remember_x(p, x_new, nid);
+  if (pri_res_norm) *pri_res_norm = std::sqrt(p->h_scal[SC_PRI2]);
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole loop on the device: optim_loop! (iterate.jl:100-266), full batch
+// ------------------------------------------------------------------------------------------------
+extern "C" int scs_solve(scs_problem* p, const double* x0, const double* x_star, int64_t max_epoch, double x_tol,
+                         double f_tol, double* x_out, double* obj, double* fval, double* pri_res_norm, double* rel,
+                         double* objrel, int64_t* n_hist, int64_t* epochs_out) {
+  SCS_TRY(check_ready(p));
+  if (!p->has_sm) return fail(SCS_STATE_ERROR, "scs_set_smoother has not been called");
+  if (!p->has_method) return fail(SCS_STATE_ERROR, "scs_set_method has not been called");
+  if (!x0 || !x_out || !n_hist || !epochs_out) return fail(SCS_INVALID_ARG, "NULL argument");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  const int m = (int)p->m;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<double> zeros(m, 0.0);
+  const double* xs = x_star ? x_star : zeros.data();
+  CU_TRY(cudaMemcpyAsync(p->d_xstar, xs, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  double nxstar = 0;
+  for (int i = 0; i < m; ++i) nxstar += xs[i] * xs[i];
+  nxstar = std::sqrt(nxstar);
+  const bool gl = p->reg.kind == SCS_REG_GL;
+  int64_t nh = 0, epochs = 0;
+  auto push = [&](double o, double f, double pr, double re, double fr) {
+    if (obj) obj[nh] = o;
+    if (fval) fval[nh] = f;
+    if (pri_res_norm) pri_res_norm[nh] = pr;
+    if (rel) rel[nh] = re;
+    if (objrel) objrel[nh] = fr;
+    ++nh;
+  };
+  // fetch objective pieces of x (loss sum, reg, ‖x−x*‖², ‖x‖²) -> host
+  auto objective_at = [&](XRef v, double* f_out, double* reg_out, double* err2, double* nx2) -> int {
+    SCS_TRY(objective_device(p, v));
+    LAUNCH(c, k_bb, 1, kVecThreads, 0, v.d, p->d_xstar, v.d, p->d_xstar, m, p->d_scal);  // SC_GG = ‖v−x*‖²
+    LAUNCH(c, k_dot, 1, kVecThreads, 0, v.d, v.d, m, p->d_scal, (int)SC_NX2);
+    CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(p->h_scal + SC_COUNT, p->d_gl + p->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SCS_TRY(ctx_sync(c));
+    *f_out = fval_from_sum(p, p->h_scal[SC_COUNT]);
+    *reg_out = p->h_scal[SC_REGX];
+    *err2 = p->h_scal[SC_GG];
+    *nx2 = p->h_scal[SC_NX2];
+    return SCS_OK;
+  };
+  auto rel_err = [&](double err2) {  // iterate.jl:192-197
+    if (gl) return err2 / (double)m;
+    return std::max(std::sqrt(err2) / std::max(nxstar, 1.0), x_tol);
+  };
+  double obj_star;
+  {
+    XRef s{p->d_xstar, p->next_id++};
+    double f, r, e2, n2;
+    SCS_TRY(objective_at(s, &f, &r, &e2, &n2));
+    obj_star = f + r;  // iterate.jl:179
+  }
+  auto frel = [&](double o) {  // iterate.jl:200 (NaN-propagating max)
+    const double v = std::fabs(o - obj_star) / std::fabs(obj_star);
+    return (v != v) ? v : std::max(v, f_tol);
+  };
+  int cur = 0, prv = 1, nxt = 2;
+  CU_TRY(cudaMemcpyAsync(p->vx[cur], x0, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->vx[prv], x0, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  uint64_t id_cur = p->next_id++, id_prv = id_cur;
+  SCS_TRY(scs_method_init(p));
+  double pri = nan, f_rel_error = 0;
+  for (int64_t epoch_t = 1; epoch_t <= max_epoch; ++epoch_t) {
+    XRef xc{p->vx[cur], id_cur}, xp{p->vx[prv], id_prv};
+    double f, r, e2, nx2;
+    SCS_TRY(objective_at(xc, &f, &r, &e2, &nx2));
+    double o = f + r;
+    f_rel_error = frel(o);
+    push(o, f, pri, rel_err(e2), f_rel_error);
+    if (epoch_t == max_epoch) push(o, f, pri, rel_err(e2), f_rel_error);  // iterate.jl:219-231 (same values again)
+    const uint64_t id_new = p->next_id++;
+    SCS_TRY(step_device(p, xc, xp, epoch_t, p->vx[nxt], id_new, p->d_xstar));
+    CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SCS_TRY(ctx_sync(c));
+    pri = std::sqrt(p->h_scal[SC_PRI2]);
+    const double diff = std::sqrt(p->h_scal[SC_DIFF2]);
+    const double nx = std::sqrt(nx2);
+    const bool stop = diff < x_tol * std::max(nx, 1.0) || f_rel_error <= f_tol || pri < x_tol;  // :234
+    XRef xn{p->vx[nxt], id_new};
+    if (stop) {
+      if (epoch_t != max_epoch) {  // :235-247
+        double f2, r2, e22, n22;
+        SCS_TRY(objective_at(xn, &f2, &r2, &e22, &n22));
+        const double o2 = f2 + r2;
+        f_rel_error = frel(o2);
+        push(o2, f2, pri, rel_err(e22), f_rel_error);
+      }
+      epochs += 1;
+    }
+    // x_prev = x; x = x_new
+    const int old_prv = prv;
+    prv = cur;
+    id_prv = id_cur;
+    cur = nxt;
+    id_cur = id_new;
+    nxt = old_prv;
+    // :257 — ‖x − x_prev‖ is the same ‖x⁺ − x‖ computed above
+    if (diff < x_tol * std::max(nx, 1.0) || f_rel_error <= f_tol || pri < x_tol) break;
+    epochs += 1;
+  }
+  CU_TRY(cudaMemcpyAsync(x_out, p->vx[cur], m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  *n_hist = nh;
+  *epochs_out = epochs;
+  return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported: component entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int scs_loss_eval(scs_problem* p, const double* x, int weight_kind, double* fval, double* grad, double* z,
+                             double* r, double* w) {
+  if (!p || !x) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (weight_kind < 0 || weight_kind > 1) return fail(SCS_INVALID_ARG, "unknown weight_kind");
+  if (weight_kind == SCS_WEIGHTS_GGN && p->loss.kind == SCS_LOSS_QUADFORM)
+    return fail(SCS_UNSUPPORTED, "quadform loss has no out_fn / GGN weights");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  XRef xr;
+  SCS_TRY(intern_x(p, x, p->vx[0], &xr));
+  if (grad)
+    SCS_TRY(ensure_grad(p, xr, weight_kind));
+  else
+    SCS_TRY(ensure_loss(p, xr, weight_kind));
+  CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_gl + p->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (grad) CU_TRY(cudaMemcpyAsync(grad, p->d_gl, p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (z) CU_TRY(cudaMemcpyAsync(z, p->dz, p->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (r) CU_TRY(cudaMemcpyAsync(r, p->dr, p->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (w) CU_TRY(cudaMemcpyAsync(w, p->dw, p->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  if (fval) *fval = fval_from_sum(p, p->h_scal[0]);
+  return SCS_OK;
+}
+
+extern "C" int scs_gram(scs_problem* p, const double* x, int weight_kind, double* G) {
+  if (!p || !x || !G) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (weight_kind < 0 || weight_kind > 1) return fail(SCS_INVALID_ARG, "unknown weight_kind");
+  if (weight_kind == SCS_WEIGHTS_GGN && p->loss.kind == SCS_LOSS_QUADFORM)
+    return fail(SCS_UNSUPPORTED, "quadform loss has no out_fn / GGN weights");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  XRef xr;
+  SCS_TRY(intern_x(p, x, p->vx[0], &xr));
+  SCS_TRY(ensure_forward(p, xr, weight_kind));
+  SCS_TRY(run_gram(p, xr));
+  CU_TRY(cudaMemcpyAsync(G, p->d_G, (size_t)p->m * p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  return SCS_OK;
+}
+
+extern "C" int scs_linear_solve(scs_ctx* c, const double* M, const double* b, int64_t m64, double* d,
+                                int* used_fallback) {
+  if (!c || !M || !b || !d) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (m64 < 1 || m64 > 65536) return fail(SCS_INVALID_ARG, "m out of range");
+  CU_TRY(cudaSetDevice(c->device));
+  const int m = (int)m64;
+  double *dM = nullptr, *dS = nullptr, *dL = nullptr, *db = nullptr, *dt = nullptr, *dd = nullptr;
+  int* di = nullptr;
+  const int nblk = (m + kNB - 1) / kNB;
+  int rc = SCS_OK;
+  auto cleanup = [&]() {
+    dfree(dM), dfree(dS), dfree(dL), dfree(db), dfree(dt), dfree(dd), dfree(di);
+  };
+  if ((rc = dalloc(&dM, (size_t)m * m)) || (rc = dalloc(&dS, (size_t)m * m)) ||
+      (rc = dalloc(&dL, (size_t)nblk * kNB * kNB)) || (rc = dalloc(&db, m)) || (rc = dalloc(&dt, m)) ||
+      (rc = dalloc(&dd, m))) {
+    cleanup();
+    return rc;
+  }
+  if (cudaMalloc((void**)&di, sizeof(int)) != cudaSuccess) {
+    cleanup();
+    return fail(SCS_OOM, "cudaMalloc failed");
+  }
+  cudaMemcpyAsync(dM, M, (size_t)m * m * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(db, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  int fb = 0;
+  rc = run_solve(c, dM, dS, dL, di, db, dt, dd, m, &fb);
+  if (rc == SCS_OK) {
+    cudaMemcpyAsync(d, dd, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    rc = ctx_sync(c);
+  }
+  if (used_fallback) *used_fallback = fb;
+  cleanup();
+  return rc;
+}
+
+extern "C" int scs_smoother_eval(scs_problem* p, const double* x, double* gr, double* hr) {
+  if (!p || !x) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (!p->has_sm) return fail(SCS_STATE_ERROR, "scs_set_smoother has not been called");
+  if ((p->sm.kind == SCS_SMOOTH_PHUBER_GL || p->sm.kind == SCS_SMOOTH_OSBA_GL) && !p->sm.cdiag)
+    return fail(SCS_STATE_ERROR, "GL smoothers need scs_set_regularizer(gl) first (they read model.P)");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMemcpyAsync(p->d_trial, x, p->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_smoother, 1, kVecThreads, 0, p->sm, p->d_trial, (int)p->m, p->d_t1, p->d_t2);
+  if (gr) CU_TRY(cudaMemcpyAsync(gr, p->d_t1, p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (hr) CU_TRY(cudaMemcpyAsync(hr, p->d_t2, p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return ctx_sync(c);
+}
+
+extern "C" int scs_prox(scs_problem* p, const double* u, const double* hr, double ss, double* out) {
+  SCS_TRY(check_ready(p));
+  if (!u || !hr || !out) return fail(SCS_INVALID_ARG, "NULL argument");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMemcpyAsync(p->d_trial, u, p->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(p->d_t2, hr, p->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_prox, 1, kVecThreads, 0, p->reg, ss, p->d_t2, p->d_trial, (int)p->m);
+  CU_TRY(cudaMemcpyAsync(out, p->d_trial, p->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return ctx_sync(c);
+}
+
+extern "C" int scs_reg_value(scs_problem* p, const double* x, double* out) {
+  SCS_TRY(check_ready(p));
+  if (!x || !out) return fail(SCS_INVALID_ARG, "NULL argument");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMemcpyAsync(p->d_trial, x, p->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_reg, 1, kVecThreads, 0, p->reg, p->d_trial, (int)p->m, p->d_scal + SC_REGX);
+  CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal + SC_REGX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SCS_TRY(ctx_sync(c));
+  *out = p->h_scal[0];
+  return SCS_OK;
+}

@@ -1,0 +1,532 @@
+"""Host-side mirror of the reference's operator interface for the proximal-SCORE hot path.
+
+Same names, argument meaning and error behaviour as SelfConcordantSmoothOptimization.jl, so the parity tests
+read like the reference's own tests (test/test_algs.jl):
+
+    model = Problem(A, y, x0, LogisticLoss(1/5), 1)                       # src/problems.jl:61-81
+    sol   = iterate(ProxNSCORE(), model, "l1", PHuberSmootherL1L2(1))     # src/algorithms/iterate.jl:56-76
+
+Everything numeric runs in libscs_b200.so on the GPU; this file only holds the epoch loop bookkeeping of
+optim_loop! (iterate.jl:100-266: histories, stopping rules) — the part the survey keeps on the host — and
+argument marshalling.  julia/SCSB200.jl mirrors it 1:1 over the same C symbols.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _capi as K
+from ._capi import ScsError, UnsupportedError
+
+
+# ---- contexts ---------------------------------------------------------------------------------
+class Context:
+    """One per (process, GPU).  world > 1: every rank passes the same 128-byte unique id."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, unique_id: Optional[bytes] = None):
+        L = K.lib()
+        h = C.c_void_p()
+        buf = None
+        if world > 1:
+            if unique_id is None or len(unique_id) != 128:
+                raise ValueError("world > 1 needs the 128-byte unique id from Context.unique_id()")
+            buf = C.create_string_buffer(unique_id, 128)
+        K.check(L.scs_ctx_create(device, rank, world, buf, C.byref(h)))
+        self._h, self.device, self.rank, self.world = h, device, rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        K.check(K.lib().scs_comm_unique_id(buf))
+        return buf.raw
+
+    def sync(self):
+        K.check(K.lib().scs_ctx_sync(self._h))
+
+    def stream(self) -> int:
+        s = C.c_uint64()
+        K.check(K.lib().scs_ctx_stream(self._h, C.byref(s)))
+        return s.value
+
+    def launches(self, reset=False) -> int:
+        v = C.c_int64()
+        K.check(K.lib().scs_get_counters(self._h, C.byref(v), int(reset)))
+        return v.value
+
+    def set_profiling(self, on: bool):
+        K.check(K.lib().scs_set_profiling(self._h, int(on)))
+
+    def stage_ms(self, reset=False):
+        ms = np.zeros(8)
+        calls = np.zeros(8, dtype=np.int64)
+        K.check(K.lib().scs_get_stage_ms(self._h, K.dptr(ms), K.iptr(calls), int(reset)))
+        return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(K.STAGES)}
+
+    def linear_solve(self, M, b):
+        """(H + λHr) \\ ∇q on the device: Cholesky, pivoted-LU fallback.  Returns (d, used_fallback)."""
+        M = np.asfortranarray(np.asarray(M, dtype=np.float64))
+        b = K.vec(b, M.shape[0])
+        d = np.empty_like(b)
+        fb = C.c_int()
+        K.check(K.lib().scs_linear_solve(self._h, K.dptr(M), K.dptr(b), M.shape[0], K.dptr(d), C.byref(fb)))
+        return d, bool(fb.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            K.lib().scs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---- built-in losses (the README / test closures) -------------------------------
+@dataclass
+class LogisticLoss:
+    """f(A,y,x)=scale*sum(log(1+exp(-y.*(A*x)))), f(y,ŷ) cross-entropy, out_fn=σ(Ax)  (README.md:113,135-139)."""
+    scale: float
+    label_mode: str = "literal"  # "literal": CE sees y as given (README feeds ±1); "consistent": (y+1)/2
+    kind = K.LOSS_LOGISTIC
+
+    def param(self):
+        return float(self.scale)
+
+    def label_code(self):
+        if self.label_mode not in ("literal", "consistent"):
+            raise ValueError("label_mode must be 'literal' or 'consistent'")
+        return K.LABELS_LITERAL if self.label_mode == "literal" else K.LABELS_CONSISTENT
+
+
+@dataclass
+class LeastSquaresLoss:
+    """f(A,y,x)=0.5*sum((A*x-y).^2)/denom, out_fn=A*x  (README.md:212-214,233-239)."""
+    denom: float
+    kind = K.LOSS_LEASTSQUARES
+
+    def param(self):
+        return float(self.denom)
+
+    def label_code(self):
+        return 0
+
+
+@dataclass
+class QuadFormLoss:
+    """f(A,y,x)=1/2*(x'*(A*x))+y'*x  (test/test_algs.jl:90).  ProxNSCORE / ProxLQNSCORE only."""
+    kind = K.LOSS_QUADFORM
+
+    def param(self):
+        return 0.0
+
+    def label_code(self):
+        return 0
+
+
+_BUILTIN = (LogisticLoss, LeastSquaresLoss, QuadFormLoss)
+
+
+class get_P:
+    """Group structure for "gl" (src/utils/prox-reg-utils.jl:9-62): ind = 3 x grpNUM (1-based start,end,weight)."""
+
+    def __init__(self, n, G, ind):
+        self.ind = np.asfortranarray(np.asarray(ind, dtype=np.int64))
+        if self.ind.ndim != 2 or self.ind.shape[0] != 3:
+            raise ValueError("ind must be 3 x grpNUM")
+        self.n = int(n)
+        self.G = np.ascontiguousarray(np.asarray(G, dtype=np.int64))
+        self.grpNUM = self.ind.shape[1]
+
+
+class Problem:
+    """Problem(A, y, x0, f, λ; L, sol, C_set, P, out_fn, ...) — src/problems.jl:61-81.
+
+    A is copied to the GPU once here (replacing the per-iteration `Matrix(As')` of iterate.jl:206-207).
+    `f` must be one of the built-in loss objects: an arbitrary callable would need ForwardDiff on the CPU and is
+    rejected explicitly.  Row-sharded use: each rank passes its own rows and a Context with world > 1.
+    """
+
+    def __init__(self, A, y, x0, f, lam, *, L=None, sol=None, C_set=None, P=None, out_fn=None, grad_fx=None,
+                 hess_fx=None, jac_yx=None, grad_fy=None, hess_fy=None, Atest=None, ytest=None, name=None, ctx=None):
+        if not isinstance(f, _BUILTIN):
+            raise UnsupportedError(K.SCS_UNSUPPORTED,
+                                   "arbitrary user f (ForwardDiff-only path) is not supported on the GPU: pass "
+                                   "LogisticLoss / LeastSquaresLoss / QuadFormLoss")
+        if any(v is not None for v in (out_fn, grad_fx, hess_fx, jac_yx, grad_fy, hess_fy)):
+            raise UnsupportedError(K.SCS_UNSUPPORTED, "user derivative closures cannot run on the GPU; the built-in "
+                                                      "losses carry their own out_fn and derivatives")
+        if Atest is not None or ytest is not None:
+            raise UnsupportedError(K.SCS_UNSUPPORTED, "Atest/ytest are not supported by the GPU path yet")
+        self.ctx = ctx or default_context()
+        self.f, self.lam, self.L, self.C_set, self.P, self.name = f, lam, L, C_set, P, name
+        self.x0 = K.vec(x0)
+        self.x = np.zeros_like(self.x0) if sol is None else K.vec(sol, self.x0.shape[0])  # problems.jl:70
+        self._h = C.c_void_p()
+        self._reg_name = None
+        if A is not None:
+            A = np.asarray(A, dtype=np.float64)
+            if A.ndim != 2:
+                raise ValueError("A must be a matrix")
+            if not A.flags["F_CONTIGUOUS"]:
+                A = np.asfortranarray(A)  # Julia's layout
+            yv = K.vec(y, A.shape[0])  # Int / Bool / Float labels all go over the wire as fp64
+            if A.shape[1] != self.x0.shape[0]:
+                raise ValueError("x0 length must equal the number of columns of A")
+            self.n, self.m = A.shape
+            K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A), self.n, self.m, A.shape[0], K.dptr(yv),
+                                               f.kind, f.param(), f.label_code(), C.byref(self._h)))
+
+    @classmethod
+    def synthetic(cls, n_total, m, f, lam, *, x0=None, row0=0, n_local=None, seed=1234, density=1.0, ctx=None, **kw):
+        """Benchmark-sized shard generated directly in HBM (oracle/synth.py twin)."""
+        self = cls(None, None, np.zeros(m) if x0 is None else x0, f, lam, ctx=ctx, **kw)
+        n_local = n_total - row0 if n_local is None else n_local
+        self.n, self.m = n_local, m
+        K.check(K.lib().scs_problem_create_synthetic(self.ctx._h, n_total, row0, n_local, m, f.kind, f.param(),
+                                                     f.label_code(), seed, density, C.byref(self._h)))
+        return self
+
+    # -- helpers -------------------------------------------------------------------------------
+    def lam_scalar(self):
+        return float(self.lam[0]) if np.ndim(self.lam) > 0 and len(self.lam) > 1 else float(np.ravel(self.lam)[0])
+
+    def read_rows(self, row0, nrows):
+        A = np.empty((nrows, self.m), order="F")
+        y = np.empty(nrows)
+        K.check(K.lib().scs_problem_read_rows(self._h, row0, nrows, K.dptr(A), K.dptr(y)))
+        return A, y
+
+    def _set_reg(self, reg_name):
+        if reg_name not in K.REG_KINDS:
+            raise ScsError(K.SCS_INVALID_ARG, "reg_name not valid.")  # prox-operators.jl:78, regularizers.jl:29
+        kind = K.REG_KINDS[reg_name]
+        lam1 = lam2 = 0.0
+        ind = perm = lb = ub = None
+        ng = nlb = nub = 0
+        if reg_name == "gl":
+            if np.ndim(self.lam) == 0 or len(self.lam) != 2:
+                raise ScsError(K.SCS_INVALID_ARG,
+                               "Please provide a Tuple or Vector with exactly two entries for λ, e.g. [λ1, λ2]")
+            if self.P is None:
+                raise ScsError(K.SCS_INVALID_ARG, "reg_name \"gl\" needs P = get_P(n, G, ind)")
+            lam1, lam2 = float(self.lam[0]), float(self.lam[1])
+            ind, ng = self.P.ind, self.P.grpNUM
+            perm = self.P.G if not np.array_equal(self.P.G, np.arange(1, self.m + 1)) else None
+        else:
+            lam1 = self.lam_scalar()
+        if reg_name == "indbox":
+            if self.C_set is None:
+                raise ScsError(K.SCS_INVALID_ARG, "reg_name \"indbox\" needs C_set = (lb, ub)")
+            lb, ub = K.vec(self.C_set[0]), K.vec(self.C_set[1])
+            nlb, nub = lb.shape[0], ub.shape[0]
+        K.check(K.lib().scs_set_regularizer(self._h, kind, lam1, lam2, K.iptr(ind), ng, K.iptr(perm), K.dptr(lb), nlb,
+                                            K.dptr(ub), nub))
+        self._reg_name = reg_name
+
+    def _set_smoother(self, h):
+        lb = ub = None
+        nlb = nub = 0
+        if getattr(h, "lb", None) is not None:
+            lb, ub = K.vec(h.lb), K.vec(h.ub)
+            nlb, nub = lb.shape[0], ub.shape[0]
+        K.check(K.lib().scs_set_smoother(self._h, h.kind, float(h.mu), K.dptr(lb), nlb, K.dptr(ub), nub))
+
+    def _set_method(self, method):
+        K.check(K.lib().scs_set_method(self._h, method.kind, int(method.ss_type), int(bool(method.use_prox)),
+                                       int(getattr(method, "m", 10))))
+        K.check(K.lib().scs_set_L(self._h, int(self.L is not None), float(self.L) if self.L is not None else 0.0))
+
+    def configure(self, method, reg_name, hmu):
+        self._set_reg(reg_name)
+        self._set_smoother(hmu)
+        if method is not None:
+            self._set_method(method)
+
+    # -- the two call sites of optim_loop! ----------------------------------------------------------
+    def objective(self, x):
+        """(model.f(A,y,x), get_reg(model,x,reg_name))  — iterate.jl:189-190."""
+        fv, rv = C.c_double(), C.c_double()
+        K.check(K.lib().scs_objective(self._h, K.dptr(K.vec(x, self.m)), C.byref(fv), C.byref(rv)))
+        return fv.value, rv.value
+
+    def step(self, x, x_prev, it, return_dx=False):
+        """step!(method, model, reg_name, hμ, As, x, x_prev, ys, Cmat, iter; return_dx) — iterate.jl:233."""
+        x = K.vec(x, self.m)
+        xp = K.vec(x_prev, self.m) if x_prev is not None else None
+        xn = np.empty(self.m)
+        dx = np.empty(self.m) if return_dx else None
+        pri = C.c_double()
+        K.check(K.lib().scs_step(self._h, K.dptr(x), K.dptr(xp), int(it), K.dptr(xn), K.dptr(dx), C.byref(pri)))
+        return (xn, dx, pri.value) if return_dx else (xn, pri.value)
+
+    # -- component entry points -----------------------------------------------------------------------
+    def loss_eval(self, x, weights="newton", want_grad=True, want_rows=False):
+        wk = K.WEIGHTS_GGN if weights == "ggn" else K.WEIGHTS_NEWTON
+        fv = C.c_double()
+        g = np.empty(self.m) if want_grad else None
+        z = r = w = None
+        if want_rows:
+            z, r, w = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        K.check(K.lib().scs_loss_eval(self._h, K.dptr(K.vec(x, self.m)), wk, C.byref(fv), K.dptr(g), K.dptr(z),
+                                      K.dptr(r), K.dptr(w)))
+        return fv.value, g, z, r, w
+
+    def gram(self, x, weights="newton"):
+        wk = K.WEIGHTS_GGN if weights == "ggn" else K.WEIGHTS_NEWTON
+        G = np.empty((self.m, self.m), order="F")
+        K.check(K.lib().scs_gram(self._h, K.dptr(K.vec(x, self.m)), wk, K.dptr(G)))
+        return G
+
+    def smoother_eval(self, x):
+        gr, hr = np.empty(self.m), np.empty(self.m)
+        K.check(K.lib().scs_smoother_eval(self._h, K.dptr(K.vec(x, self.m)), K.dptr(gr), K.dptr(hr)))
+        return gr, hr
+
+    def prox(self, u, hr, ss):
+        out = np.empty(self.m)
+        K.check(K.lib().scs_prox(self._h, K.dptr(K.vec(u, self.m)), K.dptr(K.vec(hr, self.m)), float(ss), K.dptr(out)))
+        return out
+
+    def reg_value(self, x):
+        v = C.c_double()
+        K.check(K.lib().scs_reg_value(self._h, K.dptr(K.vec(x, self.m)), C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            K.lib().scs_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ProblemGeneric(*a, **k):
+    """Problem(x0, f, λ; ...) without data (src/problems.jl:44-59): arbitrary f(x), ForwardDiff only."""
+    raise UnsupportedError(K.SCS_UNSUPPORTED,
+                           "ProblemGeneric (arbitrary f(x) differentiated by ForwardDiff) has no GPU path and is "
+                           "rejected instead of running on the CPU")
+
+
+# ---- smoothers (constants pinned by test/test_smooth.jl) ------------------------------------------
+class _Smoother:
+    lb = ub = None
+
+    def __init__(self, mu, Mh, nu):
+        self.mu, self.Mh, self.nu = mu, Mh, nu
+
+
+class PHuberSmootherL1L2(_Smoother):  # phuber-smooth.jl:6-27
+    kind = K.SMOOTH_PHUBER_L1L2
+
+    def __init__(self, mu):
+        super().__init__(mu, 2.0, 2.6)
+
+
+class PHuberSmootherIndBox(_Smoother):  # phuber-smooth.jl:38-64
+    kind = K.SMOOTH_PHUBER_INDBOX
+
+    def __init__(self, lb, ub, mu):
+        super().__init__(mu, 2.0, 2.6)
+        self.lb, self.ub = lb, ub
+
+
+class PHuberSmootherGL(_Smoother):  # phuber-smooth.jl:116-148 (takes the problem, reads model.P)
+    kind = K.SMOOTH_PHUBER_GL
+
+    def __init__(self, mu, model):
+        super().__init__(mu, 2.0, 2.6)
+        self.model = model
+
+
+class ExponentialSmootherIndBox(_Smoother):  # exponential-smooth.jl:28-34
+    kind = K.SMOOTH_EXP_INDBOX
+
+    def __init__(self, lb, ub, mu):
+        super().__init__(mu, 1.0, 2.0)
+        self.lb, self.ub = lb, ub
+
+
+class LogExpSmootherIndBox(_Smoother):  # log-exp-smooth.jl:28-34
+    kind = K.SMOOTH_LOGEXP_INDBOX
+
+    def __init__(self, lb, ub, mu):
+        super().__init__(mu, 1.0, 2.0)
+        self.lb, self.ub = lb, ub
+
+
+class OsBaSmootherL1L2(_Smoother):  # ostrovskii-bach-smooth.jl:6-27
+    kind = K.SMOOTH_OSBA_L1L2
+
+    def __init__(self, mu):
+        super().__init__(mu, 2 * np.sqrt(2), 3.0)
+
+
+class OsBaSmootherGL(_Smoother):  # ostrovskii-bach-smooth.jl:38-70
+    kind = K.SMOOTH_OSBA_GL
+
+    def __init__(self, mu, model):
+        super().__init__(mu, 2 * np.sqrt(2), 3.0)
+        self.model = model
+
+
+# ---- methods -----------------------------------------------------------------------------------
+@dataclass
+class ProxNSCORE:  # prox-N-SCORE.jl:6-33
+    ss_type: int = 1
+    use_prox: bool = True
+    name: str = "prox-newtonscore"
+    label: str = "Prox-N-SCORE"
+    kind = K.METHOD_N
+
+    def set_name(self):
+        if not self.use_prox:
+            self.name, self.label = "newtonscore", "Newton-SCORE"
+
+
+@dataclass
+class ProxGGNSCORE:  # prox-GGN-SCORE.jl:6-33
+    ss_type: int = 1
+    use_prox: bool = True
+    name: str = "prox-ggnscore"
+    label: str = "Prox-GGN-SCORE"
+    kind = K.METHOD_GGN
+
+    def set_name(self):
+        if not self.use_prox:
+            self.name, self.label = "ggnscore", "GGN-SCORE"
+
+
+@dataclass
+class ProxLQNSCORE:  # prox-L-BFGS-SCORE.jl:6-46 (s_list / y_list / H0 live on the device)
+    ss_type: int = 1
+    use_prox: bool = True
+    m: int = 10
+    name: str = "prox-lbfgsscore"
+    label: str = "Prox-LBFGS-SCORE"
+    kind = K.METHOD_LQN
+
+    def set_name(self):
+        if not self.use_prox:
+            self.name, self.label = "lbfgsscore", "LBFGS-SCORE"
+
+
+@dataclass
+class Solution:  # iterate.jl:3-32
+    x: np.ndarray
+    obj: list
+    fval: list
+    pri_res_norm: list
+    fvaltest: list
+    rel: list
+    objrel: list
+    metricvals: dict
+    times: list
+    epochs: int
+    model: object
+
+
+def _norm(v):
+    return float(np.linalg.norm(v))
+
+
+def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_size=None, slice_samples=False,
+            shuffle_batch=True, max_epoch=1000, comm_rounds=100, local_max_iter=None, x_tol=1e-10, f_tol=1e-10,
+            verbose=1, device_loop=False):
+    """iterate!(method, model, reg_name, hμ; ...) — iterate.jl:56-76 → optim_loop! :100-266 (full batch).
+
+    device_loop=False: the epoch loop runs here and calls scs_objective / scs_step once per epoch (what the Julia
+    shim does).  device_loop=True: the same loop runs inside the library (scs_solve), x never leaves HBM.
+    """
+    import time
+    if batch_size is not None or slice_samples or local_max_iter is not None:
+        raise UnsupportedError(K.SCS_UNSUPPORTED, "mini-batch / slice_samples / local_max_iter are not supported on "
+                                                  "the GPU path yet (full batch only)")
+    if metrics is not None:
+        raise UnsupportedError(K.SCS_UNSUPPORTED, "user metric callbacks would have to read A on the host")
+    method.set_name()  # iterate.jl:112
+    if alpha is not None:
+        model.L = 1 / alpha  # :113-115
+    model.configure(method, reg_name, hmu)
+    x_star = model.x
+    m = model.m
+    if device_loop:
+        cap = int(max_epoch) + 2
+        xo = np.empty(m)
+        h = [np.empty(cap) for _ in range(5)]
+        nh, ep = C.c_int64(), C.c_int64()
+        K.check(K.lib().scs_solve(model._h, K.dptr(model.x0), K.dptr(x_star), int(max_epoch), float(x_tol),
+                                  float(f_tol), K.dptr(xo), *[K.dptr(a) for a in h], C.byref(nh), C.byref(ep)))
+        k = nh.value
+        pri = [None if np.isnan(v) else float(v) for v in h[2][:k]]
+        return Solution(xo, list(h[0][:k]), list(h[1][:k]), pri, [], list(h[3][:k]), list(h[4][:k]), {}, [], ep.value,
+                        model)
+
+    objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
+    epochs = 0
+    pri_res_norm = None
+    fs, rs = model.objective(x_star)
+    with np.errstate(all="ignore"):
+        obj_star = fs + rs  # :179
+    x = model.x0.copy()
+    x_prev = x.copy()
+    K.check(K.lib().scs_method_init(model._h))  # init!(method, x) :183
+    t0 = time.perf_counter()
+
+    def rel_err(v):  # :192-197
+        if reg_name == "gl":
+            return float(np.mean((x_star - v) ** 2))
+        return max(_norm(v - x_star) / max(_norm(x_star), 1), x_tol)
+
+    def frel(o):  # :200
+        with np.errstate(all="ignore"):
+            return float(np.maximum(np.abs(np.float64(o) - obj_star) / np.abs(np.float64(obj_star)), f_tol))
+
+    def push(o, f, p, r, fr):  # utils.jl:106-113
+        objs.append(o), fvals.append(f), pris.append(p), rels.append(r), frels.append(fr)
+        times.append(time.perf_counter() - t0)
+
+    for epoch_t in range(1, int(max_epoch) + 1):
+        fval, reg = model.objective(x)
+        obj = fval + reg
+        rel_error = rel_err(x)
+        f_rel_error = frel(obj)
+        push(obj, fval, pri_res_norm, rel_error, f_rel_error)
+        if epoch_t == max_epoch:  # :219-231
+            fval, reg = model.objective(x)
+            obj = fval + reg
+            f_rel_error = frel(obj)
+            push(obj, fval, pri_res_norm, rel_err(x), f_rel_error)
+        x_new, pri_res_norm = model.step(x, x_prev, epoch_t)  # :233
+        if _norm(x_new - x) < x_tol * max(_norm(x), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :234
+            if epoch_t != max_epoch:
+                fval, reg = model.objective(x_new)
+                obj = fval + reg
+                f_rel_error = frel(obj)
+                push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error)
+            x_prev, x = x.copy(), x_new
+            epochs += 1
+        else:
+            x_prev, x = x.copy(), x_new
+        if _norm(x - x_prev) < x_tol * max(_norm(x_prev), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :257
+            break
+        epochs += 1
+    return Solution(x, objs, fvals, pris, [], rels, frels, {}, times, epochs, model)

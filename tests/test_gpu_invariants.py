@@ -1,0 +1,60 @@
+"""Size-independent properties at sizes the numpy oracle would not finish in seconds (inputs generated in HBM):
+adjoint identity <Ax, r> = <x, A'r>, Gram quadratic form u'Gu = sum w (Au)^2, linearity of the streaming pass,
+row-shard additivity (two half problems sum to the full one — the multi-GPU exchange is exactly this sum)."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_identities_large(scs):
+    n, m = 300_000, 1024
+    L = scs.LogisticLoss(1 / n, "consistent")
+    p = scs.Problem.synthetic(n, m, L, 1e-3)
+    x = synth.make_x0(m) * 0.3
+    f, g, z, r, w = p.loss_eval(x, weights="ggn", want_rows=True)
+    # adjoint identity
+    lhs, rhs = float(z @ r), float(x @ g)
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), np.linalg.norm(z) * np.linalg.norm(r))
+    # linearity of z = A x
+    _, _, z2, _, _ = p.loss_eval(2.0 * x, weights="ggn", want_grad=False, want_rows=True)
+    assert np.max(np.abs(z2 - 2.0 * z)) <= 1e-13 * np.max(np.abs(z))
+    # Gram quadratic form
+    f, g, z, r, w = p.loss_eval(x, weights="ggn", want_rows=True)
+    G = p.gram(x, weights="ggn")
+    assert np.array_equal(G, G.T)
+    u = synth.make_x0(m, seed=77)
+    _, _, zu, _, _ = p.loss_eval(u, weights="ggn", want_grad=False, want_rows=True)
+    q1, q2 = float(u @ G @ u), float(np.sum(w * zu * zu))
+    assert abs(q1 - q2) <= 1e-11 * abs(q2)
+    # consistent labels: GGN gradient == Newton gradient, weights >= 0
+    _, gn, *_ = p.loss_eval(x, weights="newton")
+    assert np.linalg.norm(g - gn) <= 1e-12 * np.linalg.norm(gn)
+    assert np.all(w >= 0)
+    # row-shard additivity (what the all-reduce sums)
+    h = n // 2 + 37
+    pa = scs.Problem.synthetic(n, m, L, 1e-3, row0=0, n_local=h)
+    pb = scs.Problem.synthetic(n, m, L, 1e-3, row0=h, n_local=n - h)
+    fa, ga, *_ = pa.loss_eval(x, weights="ggn")
+    fb, gb, *_ = pb.loss_eval(x, weights="ggn")
+    assert abs((fa + fb) - f) <= 1e-12 * abs(f)
+    assert np.linalg.norm(ga + gb - g) <= 1e-12 * np.linalg.norm(g)
+    Ga, Gb = pa.gram(x, weights="ggn"), pb.gram(x, weights="ggn")
+    assert np.max(np.abs(Ga + Gb - G)) <= 1e-12 * np.max(np.abs(G))
+    for q in (p, pa, pb):
+        q.close()
+
+
+def test_run_to_run_bitwise_reproducible(scs):
+    n, m = 50_000, 512
+    sols = []
+    for _ in range(2):
+        p = scs.Problem.synthetic(n, m, scs.LogisticLoss(1 / n, "consistent"), 1e-3, x0=synth.make_x0(m))
+        s = scs.iterate(scs.ProxGGNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=4, alpha=1, verbose=0,
+                        device_loop=True)
+        sols.append(s)
+        p.close()
+    assert np.array_equal(sols[0].x, sols[1].x)
+    assert sols[0].obj == sols[1].obj

@@ -1,0 +1,212 @@
+"""GPU parity, kernel by kernel, through the C ABI against the numpy oracle on the same seeded inputs.
+Tolerances (fp64): 1e-12 relative on streaming reductions / Gram entries (different summation order only),
+1e-13 on elementwise formulas, bit-exact for the synthetic generator and integer-like outputs."""
+import numpy as np
+import pytest
+
+from oracle import scs_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def logistic_problem(n, m, seed=3):
+    A = synth.make_A(n, m, seed=seed)
+    y = synth.make_labels_logistic(A @ synth.make_x_true(m, seed=seed + 1, frac=0.3), seed=seed + 2)
+    return A, y, synth.make_x0(m, seed=seed + 3) * 0.5
+
+
+# ragged shapes: single row, odd n, one row short of / past a 512-row CTA block, m not a multiple of anything
+SHAPES = [(1, 1), (5, 2), (100, 50), (511, 7), (513, 130), (1000, 33), (4096, 256), (3001, 257)]
+
+
+@pytest.mark.parametrize("n,m", SHAPES)
+@pytest.mark.parametrize("loss", ["logistic", "logistic_consistent", "ls"])
+def test_forward_adjoint(scs, n, m, loss):
+    A, y, x = logistic_problem(n, m)
+    if loss == "ls":
+        Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
+        y = synth.make_targets_ls(A @ synth.make_x_true(m), seed=9)
+    else:
+        mode = "consistent" if loss.endswith("consistent") else "literal"
+        Lo, Lg = O.LogisticLoss(1 / n, mode), scs.LogisticLoss(1 / n, mode)
+    p = scs.Problem(A, y, x, Lg, 0.1)
+    z = A @ x
+    for wk in ("newton", "ggn"):
+        fv, g, zg, rg, wg = p.loss_eval(x, weights=wk, want_rows=True)
+        r, w = (Lo.grad_weights(z, y), Lo.hess_weights(z, y)) if wk == "newton" else Lo.ggn_weights(z, y)
+        assert relerr(zg, z) <= 1e-13
+        assert abs(fv - Lo.f(A, y, x)) <= 1e-13 * abs(Lo.f(A, y, x))
+        np.testing.assert_allclose(rg, r, rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(wg, w, rtol=1e-11, atol=1e-300)
+        assert relerr(g, A.T @ r) <= 1e-12
+    p.close()
+
+
+@pytest.mark.parametrize("n,m", [(5, 2), (100, 50), (513, 130), (2048, 128), (3001, 257), (1024, 384)])
+@pytest.mark.parametrize("wk", ["newton", "ggn"])
+def test_gram(scs, n, m, wk):
+    A, y, x = logistic_problem(n, m)
+    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n), 0.1)  # literal labels: GGN weights are partly negative
+    Lo = O.LogisticLoss(1 / n)
+    z = A @ x
+    w = Lo.hess_weights(z, y) if wk == "newton" else Lo.ggn_weights(z, y)[1]
+    G = p.gram(x, weights=wk)
+    Gref = A.T @ (w[:, None] * A)
+    assert np.array_equal(G, G.T)  # exactly symmetric by construction
+    scale = np.sqrt(np.outer(np.diag(A.T @ (np.abs(w)[:, None] * A)), np.diag(A.T @ (np.abs(w)[:, None] * A))))
+    assert np.max(np.abs(G - Gref) / np.maximum(scale, 1e-300)) <= 1e-13
+    p.close()
+
+
+def test_quadform_loss(scs):
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((37, 37))
+    y, x = rng.standard_normal(37), rng.standard_normal(37)
+    p = scs.Problem(A, y, x, scs.QuadFormLoss(), 0.1)
+    Lo = O.QuadFormLoss()
+    fv, g, *_ = p.loss_eval(x)
+    assert abs(fv - Lo.f(A, y, x)) <= 1e-13 * abs(Lo.f(A, y, x))
+    assert relerr(g, Lo.grad(A, y, x)) <= 1e-13
+    assert relerr(p.gram(x), Lo.hess(A, y, x)) <= 1e-15
+    p.close()
+
+
+@pytest.mark.parametrize("m", [1, 2, 5, 63, 64, 65, 200, 777])
+def test_linear_solve_spd_and_indefinite(scs, m):
+    rng = np.random.default_rng(m)
+    B = rng.standard_normal((m + 3, m))
+    M = B.T @ B + 0.5 * np.eye(m)
+    b = rng.standard_normal(m)
+    ctx = scs.default_context()
+    d, fb = ctx.linear_solve(M, b)
+    assert not fb
+    assert relerr(d, np.linalg.solve(M, b)) <= 1e-11 * np.linalg.cond(M)
+    if m >= 2:  # symmetric indefinite -> Cholesky flags it and the pivoted LU runs on the device
+        Mi = M - 2.0 * np.diag(np.arange(m) % 2) * np.trace(M) / m
+        d2, fb2 = ctx.linear_solve(Mi, b)
+        assert fb2
+        assert relerr(d2, np.linalg.solve(Mi, b)) <= 1e-11 * np.linalg.cond(Mi)
+
+
+def _mk(scs, m, reg, lam, **kw):
+    A = synth.make_A(8, m)
+    return scs.Problem(A, np.ones(8), np.zeros(m), scs.LeastSquaresLoss(8.0), lam, **kw)
+
+
+@pytest.mark.parametrize("m", [1, 50, 1025, 5000])
+def test_smoothers(scs, m):
+    rng = np.random.default_rng(m)
+    x = rng.standard_normal(m) * 1.5
+    x[:: max(m // 7, 1)] = 0.0
+    lb, ub = -0.5, 0.8
+    ind = None
+    table = [
+        (scs.PHuberSmootherL1L2(0.7), O.PHuberSmootherL1L2(0.7), "l1"),
+        (scs.PHuberSmootherIndBox(lb, ub, 0.6), O.PHuberSmootherIndBox(lb, ub, 0.6), "indbox"),
+        (scs.ExponentialSmootherIndBox(lb, ub, 0.6), O.ExponentialSmootherIndBox(lb, ub, 0.6), "indbox"),
+        (scs.LogExpSmootherIndBox(lb, np.inf, 0.9), O.LogExpSmootherIndBox(lb, np.inf, 0.9), "indbox"),
+        (scs.LogExpSmootherIndBox(lb, ub, 0.2), O.LogExpSmootherIndBox(lb, ub, 0.2), "indbox"),
+        (scs.OsBaSmootherL1L2(0.7), O.OsBaSmootherL1L2(0.7), "l1"),
+    ]
+    for hg, ho, reg in table:
+        p = _mk(scs, m, reg, 0.1, C_set=(lb, ub))
+        p.configure(None, reg, hg)
+        gr, hr = p.smoother_eval(x)
+        with np.errstate(all="ignore"):
+            go, ho_ = ho.grad(None, x), ho.hess(None, x)
+        np.testing.assert_allclose(gr, go, rtol=2e-13, atol=1e-300, equal_nan=True, err_msg=type(hg).__name__)
+        np.testing.assert_allclose(hr, ho_, rtol=2e-13, atol=1e-300, equal_nan=True, err_msg=type(hg).__name__)
+        p.close()
+    # vector bounds for the box smoother
+    lbv, ubv = -np.abs(rng.standard_normal(m)) - 0.1, np.abs(rng.standard_normal(m)) + 0.1
+    p = _mk(scs, m, "indbox", 0.1, C_set=(lbv, ubv))
+    p.configure(None, "indbox", scs.PHuberSmootherIndBox(lbv, ubv, 0.6))
+    gr, hr = p.smoother_eval(x)
+    ho = O.PHuberSmootherIndBox(lbv, ubv, 0.6)
+    np.testing.assert_allclose(gr, ho.grad(None, x), rtol=2e-13)
+    np.testing.assert_allclose(hr, ho.hess(None, x), rtol=2e-13)
+    p.close()
+
+
+def _groups(m, gsz, w=1):
+    starts = list(range(1, m + 1, gsz))
+    return np.array([starts, [min(s + gsz - 1, m) for s in starts], [w + (i % 3) for i in range(len(starts))]])
+
+
+@pytest.mark.parametrize("m,gsz", [(6, 2), (256, 64), (1000, 37), (4100, 64)])
+def test_group_lasso_pieces(scs, m, gsz):
+    rng = np.random.default_rng(m)
+    ind = _groups(m, gsz)
+    perm = rng.permutation(m) + 1
+    Po, Pg = O.GroupStructure(m, perm, ind), scs.get_P(m, perm, ind)
+    lam = [1e-3, 0.3]
+    A = synth.make_A(8, m)
+    mo = O.Problem(A, np.ones(8), np.zeros(m), O.LeastSquaresLoss(8.0), lam, P=Po)
+    p = scs.Problem(A, np.ones(8), np.zeros(m), scs.LeastSquaresLoss(8.0), lam, P=Pg)
+    x = rng.standard_normal(m)
+    x[: gsz] *= 1e-3  # a group the prox will zero
+    for hg, ho in ((scs.PHuberSmootherGL(0.05, p), O.PHuberSmootherGL(0.05, mo)),
+                   (scs.OsBaSmootherGL(0.5, p), O.OsBaSmootherGL(0.5, mo))):
+        p.configure(None, "gl", hg)
+        gr, hr = p.smoother_eval(np.abs(x) + 0.1 if "OsBa" in type(hg).__name__ else x)
+        xx = np.abs(x) + 0.1 if "OsBa" in type(hg).__name__ else x
+        with np.errstate(all="ignore"):
+            np.testing.assert_allclose(gr, ho.grad(Po, xx), rtol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(hr, ho.hess(Po, xx), rtol=1e-11, equal_nan=True)
+    assert abs(p.reg_value(x) - O.get_reg(mo, x, "gl")) <= 1e-13 * abs(O.get_reg(mo, x, "gl"))
+    hrv = np.abs(rng.standard_normal(m)) + 0.2
+    out = p.prox(x, hrv, 0.8)
+    ref = O.prox_step(mo, "gl", x, 1 / hrv, lam[0], 0.8)
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-300)
+    assert np.array_equal(out != 0, ref != 0)
+    assert np.any(out == 0)
+    p.close()
+
+
+@pytest.mark.parametrize("reg", ["l1", "l2", "indbox"])
+@pytest.mark.parametrize("m", [1, 50, 3000])
+def test_prox_and_reg(scs, reg, m):
+    rng = np.random.default_rng(m + len(reg))
+    lbv, ubv = -np.abs(rng.standard_normal(m)) - 0.05, np.abs(rng.standard_normal(m)) + 0.05
+    A = synth.make_A(8, m)
+    mo = O.Problem(A, np.ones(8), np.zeros(m), O.LeastSquaresLoss(8.0), 0.37, C_set=(lbv, ubv))
+    p = scs.Problem(A, np.ones(8), np.zeros(m), scs.LeastSquaresLoss(8.0), 0.37, C_set=(lbv, ubv))
+    p.configure(None, reg, scs.PHuberSmootherL1L2(1.0))
+    u = rng.standard_normal(m) * 2
+    u[::5] = 0.0
+    hr = np.abs(rng.standard_normal(m)) + 0.1
+    out = p.prox(u, hr, 0.5)
+    with np.errstate(all="ignore"):
+        ref = O.prox_step(mo, reg, u, 1 / hr, 0.37, 0.5)
+    assert np.array_equal(out, ref)  # same operations in the same order: bit-exact
+    v = p.reg_value(u)
+    vo = O.get_reg(mo, u, reg)
+    assert (np.isinf(v) and np.isinf(vo)) or abs(v - vo) <= 1e-13 * max(abs(vo), 1e-300)
+    inside = np.clip(u, lbv, ubv)
+    assert p.reg_value(inside) == O.get_reg(mo, inside, reg) or reg != "indbox"
+    p.close()
+
+
+def test_synthetic_generator_bits(scs):
+    """The device Philox twin must reproduce oracle/synth.py bit for bit (A), and labels / targets exactly."""
+    n_total, m, row0, nl = 3000, 70, 517, 1501
+    for loss, dens in ((scs.LogisticLoss(1 / n_total), 1.0), (scs.LeastSquaresLoss(float(n_total)), 1.0),
+                       (scs.LogisticLoss(1 / n_total), 0.05)):
+        p = scs.Problem.synthetic(n_total, m, loss, 0.1, row0=row0, n_local=nl, seed=1234, density=dens)
+        Ag, yg = p.read_rows(0, nl)
+        A = synth.make_A(nl, m, seed=1234, row0=row0, n_total=n_total, density=dens)
+        assert np.array_equal(Ag, A)
+        z = A @ synth.make_x_true(m, seed=1235)
+        if isinstance(loss, scs.LogisticLoss):
+            y = synth.make_labels_logistic(z, seed=1236, row0=row0)
+            assert np.mean(yg != y) <= 1e-3  # a label may flip only if |u - sigma(z)| is at rounding level
+            assert set(np.unique(yg)) <= {-1.0, 1.0}
+        else:
+            np.testing.assert_allclose(yg, synth.make_targets_ls(z, seed=1236, row0=row0), rtol=1e-12, atol=1e-14)
+        p.close()

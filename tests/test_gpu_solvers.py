@@ -1,0 +1,153 @@
+"""End-to-end GPU parity through the reference-shaped host API (Problem / iterate / Solution).
+
+The bar (BASELINE.json north_star): relative error <= 1e-10 on x and on the objective history, identical l1
+support, same number of epochs / history entries as the oracle restatement of optim_loop!."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import scs_oracle as O
+from test_oracle_golden import load_golden
+from test_oracle_reference_fixtures import A1, Y1, X01, A2, Y2, X02, XS2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def hist_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300))) if fin.any() else 0.0
+
+
+# ---- the reference's own tests, through the GPU path (test/test_algs.jl) -----------------------------
+@pytest.mark.parametrize("method", ["ProxNSCORE", "ProxGGNSCORE", "ProxLQNSCORE"])
+@pytest.mark.parametrize("reg", ["l1", "l2"])
+def test_algs_regression_l1_l2(scs, method, reg):  # test_algs.jl:15-52
+    model = scs.Problem(A1, Y1, X01, scs.LogisticLoss(1 / 5), 1)
+    sol = scs.iterate(getattr(scs, method)(), model, reg, scs.PHuberSmootherL1L2(1), verbose=0)
+    assert np.allclose(model.x, np.zeros(2))
+    assert sol.epochs + 1 >= 1
+    assert sol.rel[-1] <= 1e-6
+    assert sol.objrel[-1] <= 1e-6
+    so = O.iterate(getattr(O, method)(), O.Problem(A1, Y1, X01, O.LogisticLoss(1 / 5), 1), reg, O.PHuberSmootherL1L2(1))
+    assert sol.epochs == so.epochs and len(sol.obj) == len(so.obj)
+    assert np.array_equal(sol.x != 0, so.x != 0)
+    model.close()
+
+
+@pytest.mark.parametrize("which", ["phuber", "exp"])
+def test_algs_indbox(scs, which):  # test_algs.jl:94-108
+    model = scs.Problem(A2, Y2, X02, scs.QuadFormLoss(), 1.0e-4, C_set=(-1.0, 1.0), sol=XS2)
+    mo = O.Problem(A2, Y2, X02, O.QuadFormLoss(), 1.0e-4, C_set=(-1.0, 1.0), sol=XS2)
+    if which == "phuber":
+        hg, ho, al = scs.PHuberSmootherIndBox(-1.0, 1.0, 0.6), O.PHuberSmootherIndBox(-1.0, 1.0, 0.6), 0.8
+    else:
+        hg, ho, al = scs.ExponentialSmootherIndBox(-1.0, 1.0, 0.6), O.ExponentialSmootherIndBox(-1.0, 1.0, 0.6), 1.0
+    sol = scs.iterate(scs.ProxNSCORE(), model, "indbox", hg, alpha=al, verbose=0)
+    assert sol.epochs + 1 >= 1
+    assert sol.rel[-1] <= 1e-3
+    assert sol.objrel[-1] <= 1e-3
+    so = O.iterate(O.ProxNSCORE(), mo, "indbox", ho, alpha=al)
+    assert sol.epochs == so.epochs
+    assert relerr(sol.x, so.x) <= TOL
+    model.close()
+
+
+def test_smooth_constants(scs):  # test_smooth.jl
+    assert scs.PHuberSmootherL1L2(1).Mh == 2.0 and scs.PHuberSmootherL1L2(1).nu == 2.6
+    assert scs.PHuberSmootherIndBox(-1.0, 1.0, 1).Mh == 2.0 and scs.PHuberSmootherIndBox(-1.0, 1.0, 1).nu == 2.6
+    assert scs.OsBaSmootherL1L2(1).Mh == 2 * np.sqrt(2) and scs.OsBaSmootherL1L2(1).nu == 3.0
+
+
+# ---- the five BASELINE configs at reduced n, vs the live oracle AND the committed golden vectors ------
+@pytest.mark.parametrize("name", cases.CASES)
+@pytest.mark.parametrize("device_loop", [False, True])
+def test_config_parity(scs, name, device_loop):
+    mo, modelo, reg, ho, kw = cases.build(name, O)
+    so = O.iterate(mo, modelo, reg, ho, **kw)
+    mg, modelg, reg, hg, kw = cases.build(name, scs)
+    sg = scs.iterate(mg, modelg, reg, hg, verbose=0, device_loop=device_loop, **kw)
+    g = load_golden(name)
+    tol = TOL if name != "c2b_logreg_ggn_literal" else 1e-7  # indefinite Gram, diverging iterates: ill-conditioned
+    assert sg.epochs == so.epochs == g["epochs"]
+    assert len(sg.obj) == len(so.obj)
+    assert relerr(sg.x, so.x) <= tol, relerr(sg.x, so.x)
+    assert relerr(sg.x, g["x"]) <= tol
+    assert hist_err(sg.obj, so.obj) <= tol
+    assert hist_err(sg.obj, g["obj"]) <= tol
+    assert hist_err(sg.fval, so.fval) <= tol
+    assert hist_err(sg.rel, so.rel) <= 1e-8
+    pg = [np.nan if v is None else v for v in sg.pri_res_norm]
+    po = [np.nan if v is None else v for v in so.pri_res_norm]
+    assert np.isnan(pg[0]) and np.isnan(po[0])
+    np.testing.assert_allclose(pg[1:], po[1:], rtol=1e-7, atol=1e-14)
+    if reg in ("l1", "gl"):
+        assert [int(i) for i in np.nonzero(sg.x)[0]] == g["support"]
+    modelg.close()
+
+
+def test_first_step_matches_golden(scs):
+    """One step! through scs_step (return_dx=True) against the golden first iterate of every config."""
+    for name in cases.CASES:
+        g = load_golden(name)
+        mg, modelg, reg, hg, kw = cases.build(name, scs)
+        mg.set_name()
+        if kw.get("alpha") is not None:
+            modelg.L = 1 / kw["alpha"]
+        modelg.configure(mg, reg, hg)
+        x0 = modelg.x0
+        xn, dx, pri = modelg.step(x0, x0.copy(), 1, return_dx=True)
+        assert relerr(xn, g["x_after_step1"]) <= TOL, name
+        assert abs(pri - np.linalg.norm(xn - x0)) <= 1e-12 * max(pri, 1e-300)
+        assert np.all(np.isfinite(dx))
+        modelg.close()
+
+
+@pytest.mark.parametrize("method", ["ProxNSCORE", "ProxGGNSCORE", "ProxLQNSCORE"])
+def test_linesearch_and_noprox(scs, method):
+    """ss_type=3 (Armijo, utils.jl:27-35) and use_prox=false."""
+    A, y, x0 = cases.data("c3_logreg_lqn_l1")
+    n = A.shape[0]
+    for kwm in (dict(ss_type=3), dict(use_prox=False)):
+        mo = getattr(O, method)(**kwm)
+        mg = getattr(scs, method)(**kwm)
+        po = O.Problem(A, y, x0, O.LogisticLoss(1 / n, "consistent"), 1e-2)
+        pg = scs.Problem(A, y, x0, scs.LogisticLoss(1 / n, "consistent"), 1e-2)
+        so = O.iterate(mo, po, "l1", O.PHuberSmootherL1L2(1.0), max_epoch=5, alpha=0.9)
+        sg = scs.iterate(mg, pg, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=5, alpha=0.9, verbose=0)
+        assert sg.epochs == so.epochs
+        assert relerr(sg.x, so.x) <= TOL, (method, kwm, relerr(sg.x, so.x))
+        assert hist_err(sg.obj, so.obj) <= TOL
+        pg.close()
+
+
+def test_error_behaviour(scs):
+    A, y, x0 = cases.data("c1_readme_logreg_n")
+    p = scs.Problem(A, y, x0, scs.LogisticLoss(1 / 50), 0.1)
+    with pytest.raises(scs.ScsError, match="reg_name not valid"):  # prox-operators.jl:78
+        scs.iterate(scs.ProxNSCORE(), p, "l3", scs.PHuberSmootherL1L2(1.0), verbose=0)
+    with pytest.raises(scs.ScsError, match="exactly two entries"):  # regularizers.jl:21-23
+        scs.iterate(scs.ProxNSCORE(), p, "gl", scs.PHuberSmootherL1L2(1.0), verbose=0)
+    with pytest.raises(scs.ScsError, match="ss_type in"):  # prox-N-SCORE.jl:89
+        scs.iterate(scs.ProxNSCORE(ss_type=7), p, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0)
+    with pytest.raises(scs.ScsError, match="positive"):  # smoothing.jl:15
+        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(-1.0), verbose=0)
+    with pytest.raises(scs.UnsupportedError):  # ss_type=2 is broken upstream for N/GGN (quirk 5)
+        scs.iterate(scs.ProxGGNSCORE(ss_type=2), p, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=3, verbose=0)
+    with pytest.raises(scs.ScsError, match="bounds"):  # prox-reg-utils.jl:154
+        p.C_set = (-1.0, 1.0)
+        scs.iterate(scs.ProxNSCORE(), p, "indbox", scs.PHuberSmootherIndBox(np.zeros(3), np.ones(3), 1.0), verbose=0)
+    with pytest.raises(scs.UnsupportedError):  # mini-batching: not on the GPU path yet
+        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), batch_size=10, verbose=0)
+    with pytest.raises(scs.UnsupportedError):  # GGN underdetermined branch
+        pw = scs.Problem(A[:10], y[:10], x0, scs.LogisticLoss(1 / 50), 0.1)
+        scs.iterate(scs.ProxGGNSCORE(), pw, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0)
+    p.close()
