@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — iterations/sec of the proximal-SCORE hot path on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): dense logistic regression
+n = 1,000,000 x m = 4096, fp64, ProxGGNSCORE (ss_type 1, alpha = 1), l1 (lambda = 1e-3), PHuberSmootherL1L2(1.0),
+consistent labels.  A "step" is one solver iteration = objective f(x)+g(x) (iterate.jl:189-190) + step!
+(iterate.jl:233).  With --gpus N the rows are sharded over N ranks (strong scaling: the problem is fixed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+
+  value   K iterations inside the library (scs_solve: x never leaves HBM), timed with CUDA events on the
+          library's stream, barrier + synchronize on both sides, max over ranks.
+  e2e     the same K iterations through the reference-facing calls (scs_objective + scs_step) with pinned HOST
+          buffers for x / x_prev / x_new; the per-step host<->device copies are inside the timed region.
+          A itself is uploaded once at Problem creation (like the reference keeps A in the Problem), not per step.
+  roofline       dominant kernel k_gram: n*m*(m+1) flops per launch / mean launch time (CUDA events around every
+                 launch, taken inside the timed region) against the FP64 tensor peak measured live with cuBLAS DGEMM.
+  roofline_stream  the HBM-bound forward / adjoint passes: 8*n*m bytes per pass against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline   the numpy oracle (a port: julia is not in the image) on the host cores over a bounded row sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "selfconcordantsmoothoptimization.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (n, m, loss, method, reg, description)
+    "c2": dict(n=1_000_000, m=4096, loss="logistic", method="ggn", reg="l1",
+               desc="C2 dense logistic regression n=1000000 x m=4096 fp64, ProxGGNSCORE, l1"),
+    "c3": dict(n=8_000_000, m=2048, loss="logistic", method="lqn", reg="l1",
+               desc="C3 logistic regression n=8000000 x m=2048 fp64, ProxLQNSCORE(m=10), l1"),
+    "c4": dict(n=2_000_000, m=8192, loss="ls", method="ggn", reg="gl",
+               desc="C4 sparse-group-lasso least squares n=2000000 x m=8192, groups of 64, ProxGGNSCORE"),
+    "c5": dict(n=4_000_000, m=4096, loss="ls", method="n", reg="indbox",
+               desc="C5 box-constrained least squares n=4000000 x m=4096, ProxNSCORE"),
+}
+METRIC = "iters/sec, ProxGGNSCORE 1M×4096 fp64 logreg at 1/2/4/8 B200; % HBM/FP64 roofline"
+
+
+def build_problem(S, wl, n_total, row0, n_local, ctx, x0):
+    n, m = n_total, wl["m"]
+    if wl["loss"] == "logistic":
+        loss = S.LogisticLoss(1.0 / n, "consistent")
+    else:
+        loss = S.LeastSquaresLoss(float(n))
+    kw = {}
+    if wl["reg"] == "l1":
+        lam = 1e-3
+    elif wl["reg"] == "gl":
+        lam = [1e-8, 1e-2]
+        ng = m // 64
+        ind = np.array([[g * 64 + 1 for g in range(ng)], [(g + 1) * 64 for g in range(ng)], [1] * ng])
+        kw["P"] = S.get_P(m, np.arange(1, m + 1), ind)
+    else:
+        lam = 1e-4
+        kw["C_set"] = (-0.5, 0.5)
+    model = S.Problem.synthetic(n_total, m, loss, lam, x0=x0, row0=row0, n_local=n_local, seed=1234, ctx=ctx, **kw)
+    if wl["method"] == "ggn":
+        method = S.ProxGGNSCORE()
+    elif wl["method"] == "lqn":
+        method = S.ProxLQNSCORE(m=10)
+    else:
+        method = S.ProxNSCORE()
+    if wl["reg"] == "gl":
+        hmu = S.PHuberSmootherGL(1e-2, model)
+    elif wl["reg"] == "indbox":
+        hmu = S.PHuberSmootherIndBox(-0.5, 0.5, 0.6)
+    else:
+        hmu = S.PHuberSmootherL1L2(1.0)
+    alpha = 0.8 if wl["reg"] == "indbox" else 1.0
+    return method, model, wl["reg"], hmu, alpha
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def fp64_peak_tflops(torch, dev):
+    """cuBLAS DGEMM 8192^3 (torch.matmul): best-of-5 burst and a ~1.5 s back-to-back sustained figure."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    flops = 2.0 * n ** 3
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    reps = max(3, int(1.5 * best * 1e12 / flops))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = reps * flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b, c
+    torch.cuda.empty_cache()
+    return best, sustained
+
+
+def cpu_iteration_time(A, y, x0, wl, n_total, steps=2):
+    """Wall time of oracle iterations (objective + step!) on a row sample; returns (seconds per iteration on the
+    sample, seconds of the n-independent m x m solve inside it)."""
+    from oracle import scs_oracle as O
+    n_s, m = A.shape
+    # the sample is a self-consistent problem of n_s rows (scale 1/n_s): same arithmetic per row as the full one
+    if wl["loss"] == "logistic":
+        loss = O.LogisticLoss(1.0 / n_s, "consistent")
+    else:
+        loss = O.LeastSquaresLoss(float(n_s))
+    kw = {}
+    if wl["reg"] == "l1":
+        lam = 1e-3
+    elif wl["reg"] == "gl":
+        lam = [1e-8, 1e-2]
+        ng = m // 64
+        ind = np.array([[g * 64 + 1 for g in range(ng)], [(g + 1) * 64 for g in range(ng)], [1] * ng])
+        kw["P"] = O.GroupStructure(m, np.arange(1, m + 1), ind)
+    else:
+        lam = 1e-4
+        kw["C_set"] = (-0.5, 0.5)
+    model = O.Problem(A, y, x0, loss, lam, **kw)
+    model.L = 1.0 if wl["reg"] != "indbox" else 1 / 0.8
+    method = {"ggn": O.ProxGGNSCORE, "lqn": lambda: O.ProxLQNSCORE(m=10), "n": O.ProxNSCORE}[wl["method"]]()
+    hmu = (O.PHuberSmootherGL(1e-2, model) if wl["reg"] == "gl" else
+           O.PHuberSmootherIndBox(-0.5, 0.5, 0.6) if wl["reg"] == "indbox" else O.PHuberSmootherL1L2(1.0))
+    Cmat = model.P if wl["reg"] == "gl" else None
+    method.init(x0)
+    x, xp = x0.copy(), x0.copy()
+    ts = []
+    for it in range(1, steps + 2):
+        t0 = time.perf_counter()
+        _ = model.f.f(model.A, model.y, x) + O.get_reg(model, x, wl["reg"])
+        xn, _pri = method.step(model, wl["reg"], hmu, x, xp, Cmat, it)
+        ts.append(time.perf_counter() - t0)
+        xp, x = x, xn
+    t_iter = float(np.mean(ts[1:]))  # first iteration warms up BLAS threads
+    t_solve = 0.0
+    if wl["method"] != "lqn":
+        M = np.eye(m) + 1e-3 * (A[:m].T @ A[:m] if n_s >= m else np.eye(m))
+        t0 = time.perf_counter()
+        np.linalg.solve(M, x0)
+        t_solve = time.perf_counter() - t0
+    return t_iter, t_solve
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_rows(wl):
+    # ~10-30 s of CPU work: Gram flops 2*n_s*m^2 at O(100) GFLOP/s
+    if wl["method"] == "lqn":
+        return 200_000
+    return max(2048, int(6e11 / (2.0 * wl["m"] ** 2)) // 1024 * 1024)
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU path (numpy oracle port; julia is absent) on the host cores, on a
+    bounded row sample of the same workload, extrapolated linearly in n (every n-dependent cost on this path is
+    linear in n; the m x m solve is added unscaled)."""
+    if rank != 0:
+        return
+    from oracle import synth
+    n, m = wl["n"], wl["m"]
+    n_s = cpu_sample_rows(wl)
+    A = synth.make_A(n_s, m, seed=1234, row0=0, n_total=n)
+    xt = synth.make_x_true(m, seed=1235)
+    z = A @ xt
+    y = synth.make_labels_logistic(z, seed=1236) if wl["loss"] == "logistic" else synth.make_targets_ls(z, seed=1236)
+    x0 = synth.make_x0(m, seed=1237)
+    t_iter, t_solve = cpu_iteration_time(A, y, x0, wl, n, steps=max(1, min(args.steps, 3)))
+    t_full = (t_iter - t_solve) * (n / n_s) + t_solve
+    val = 1.0 / t_full
+    cores = host_cores()
+    sample = (f"numpy/OpenBLAS oracle port, first {n_s} of {n} rows (same generator/seed), {cores} host threads; "
+              f"measured {t_iter:.3f} s/iter on the sample (solve {t_solve:.3f} s), extrapolated linearly in n")
+    line = {"metric": METRIC, "value": val, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": wl["desc"], "n": n, "m": m, "sample_rows": n_s, "extrapolated": True},
+            "cpu_baseline": {"value": val, "unit": "iters/sec", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override n (debug only; invalidates the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.rows:
+        wl["n"] = args.rows
+        wl["desc"] += f" [DEBUG rows={args.rows}]"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import scs_b200 as S
+    from oracle import synth  # x0 generator only (host side, m doubles)
+    if world != args.gpus:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = S.context_from_env()
+    n, m = wl["n"], wl["m"]
+    row0, n_local = S.shard_rows(n, world, rank)
+    x0 = synth.make_x0(m, seed=1237)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_burst, peak_sus = fp64_peak_tflops(torch, dev)
+    t_up0 = time.perf_counter()
+    method, model, reg, hmu, alpha = build_problem(S, wl, n, row0, n_local, ctx, x0)
+    ctx.sync()
+    t_gen = time.perf_counter() - t_up0
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    K, W = args.steps, args.warmup
+
+    def solve(steps):  # K iterations inside the library; tolerances 0 => never stops early
+        return S.iterate(method, model, reg, hmu, alpha=alpha, max_epoch=steps, x_tol=0.0, f_tol=0.0, verbose=0,
+                         device_loop=True)
+
+    # ---- warm-up (untimed) then the timed region for `value`
+    solve(max(W, 1))
+    ctx.set_profiling(True)
+    ctx.stage_ms(reset=True)
+    ctx.launches(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    sol = solve(K)
+    e1.record(ext)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches()
+    stages = ctx.stage_ms(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.set_profiling(False)
+
+    # ---- e2e: reference-facing calls with pinned host buffers, copies inside the timed region
+    hx = torch.empty(m, dtype=torch.float64).pin_memory()
+    hxp = torch.empty(m, dtype=torch.float64).pin_memory()
+    hx.numpy()[:] = x0
+    hxp.numpy()[:] = x0
+    method.set_name()
+    model.L = 1 / alpha
+    model.configure(method, reg, hmu)
+    S._capi.check(S._capi.lib().scs_method_init(model._h))
+    x, xp = hx.numpy(), hxp.numpy()
+    for it in range(1, W + 1):
+        model.objective(x)
+        xn, _ = model.step(x, xp, it)
+        xp[:] = x
+        x[:] = xn
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for it in range(W + 1, W + K + 1):
+        fv, rv = model.objective(x)
+        xn, pri = model.step(x, xp, it)
+        xp[:] = x
+        x[:] = xn
+        last = fv + rv
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(tt[0]), float(tt[1])
+        ll = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ll)
+        launches = int(ll[0])
+    h2d = 3 * m * 8  # x for scs_objective, x and x_prev for scs_step
+    d2h = m * 8 + 16 * 8 + 2 * 8  # x_new + scalar block + (loss, reg)
+
+    if rank == 0:
+        hbm = 6650.0
+        peaks_src = "fallback (B200_PROFILING.md)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm, peaks_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+        g_ms, g_calls = stages["gram"]
+        f_ms, f_calls = stages["forward"]
+        a_ms, a_calls = stages["adjoint"]
+        nl = n_local
+        roof = None
+        if g_calls:
+            flops = float(nl) * m * (m + 1)
+            ach = flops / (g_ms / g_calls * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_gram (DMMA.8x8x4 SYRK, TMA-fed)", "achieved": ach, "peak": peak_sus,
+                    "unit": "TFLOP/s", "frac": ach / peak_sus, "traffic": None,
+                    "peak_source": "fp64 cuBLAS DGEMM 8192^3 via torch.matmul, sustained (back-to-back ~1.5 s), measured live "
+                                   f"in this run; burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)",
+                    "algorithmic_flops_per_launch": flops, "ms_per_launch": g_ms / g_calls, "launches_timed": g_calls}
+        stream = {}
+        for nm, (s_ms, s_calls) in (("forward", (f_ms, f_calls)), ("adjoint", (a_ms, a_calls))):
+            if s_calls:
+                by = 8.0 * nl * m
+                ach = by / (s_ms / s_calls * 1e-3) / 1e9
+                stream[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                              "algorithmic_bytes_per_launch": by, "ms_per_launch": s_ms / s_calls,
+                              "launches_timed": s_calls, "peak_source": peaks_src}
+        if roof is None and stream:  # LQN workloads: the streaming pass is the dominant kernel
+            k = "forward" if "forward" in stream else "adjoint"
+            roof = dict(stream[k], kernel="k_" + k, traffic=None)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_s = min(cpu_sample_rows(wl), n_local)
+            As, ys = model.read_rows(0, n_s)
+            t_iter, t_solve = cpu_iteration_time(As, ys, x0, wl, n, steps=2)
+            t_full = (t_iter - t_solve) * (n / n_s) + t_solve
+            cpu = {"value": 1.0 / t_full, "unit": "iters/sec", "cores": host_cores(), "kind": "port",
+                   "sample": f"numpy/OpenBLAS oracle port on the first {n_s} of {n} rows read back from HBM, "
+                             f"{t_iter:.3f} s/iter on the sample (solve {t_solve:.3f} s), extrapolated linearly in n"}
+        line = {"metric": METRIC, "value": K / (ms * 1e-3), "unit": "iters/sec", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "n": n, "m": m, "rows_per_gpu": n_local, "parallelism": f"rows/{world}",
+                           "l2_policy": f"inputs larger than L2: A shard is {8.0 * n_local * m / 1e9:.1f} GB vs 126 MB L2",
+                           "generate_s": t_gen, "objective_last": last, "epochs_timed": sol.epochs},
+                "e2e": {"value": K / t_e2e, "unit": "iters/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * t_e2e / K},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_stream": stream,
+                "stages_ms_per_step": {k: v[0] / K for k, v in stages.items() if v[1]},
+                "cpu_baseline": cpu, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sus}}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

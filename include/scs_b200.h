@@ -141,7 +141,7 @@ int scs_reg_value(scs_problem* p, const double* x, double* out);
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation / last reset, and device milliseconds of the last
  * scs_step / scs_objective broken down by stage.  stage ids: 0 forward, 1 adjoint, 2 gram, 3 solve, 4 vector,
- * 5 allreduce, 6 fused forward+adjoint. */
+ * 5 allreduce, 6 fused forward+adjoint, 7 gram finalize (split sum + mirror). */
 int scs_get_counters(scs_ctx* ctx, int64_t* launches, int reset);
 int scs_set_profiling(scs_ctx* ctx, int enable);
 int scs_get_stage_ms(scs_ctx* ctx, double* ms8, int64_t* calls8, int reset);

@@ -50,7 +50,7 @@ static NcclApi g_nccl;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-enum { ST_FWD = 0, ST_ADJ = 1, ST_GRAM = 2, ST_SOLVE = 3, ST_VEC = 4, ST_COMM = 5, ST_FUSED = 6, ST_N = 8 };
+enum { ST_FWD = 0, ST_ADJ = 1, ST_GRAM = 2, ST_SOLVE = 3, ST_VEC = 4, ST_COMM = 5, ST_FUSED = 6, ST_GRAMFIN = 7, ST_N = 8 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -369,6 +369,9 @@ static int run_gram(scs_problem* p, XRef x) {
     StageTimer t(c, ST_GRAM);
     const int grid = (int)std::min<int64_t>(c->num_sms, p->plan.units);
     LAUNCH(c, k_gram, grid, kGThreads, kGSmemBytes, p->amap, p->dw, m, p->ldp, p->plan, p->d_partial);
+  }
+  {
+    StageTimer t(c, ST_GRAMFIN);
     const int t32 = (m + 31) / 32;
     LAUNCH(c, k_gram_finalize, t32 * (t32 + 1) / 2, 256, 0, p->d_partial, p->plan.splits, m, p->ldp, p->d_G);
   }

@@ -21,7 +21,7 @@ REG_KINDS = {"l1": 0, "l2": 1, "indbox": 2, "gl": 3}
 SMOOTH_PHUBER_L1L2, SMOOTH_PHUBER_INDBOX, SMOOTH_PHUBER_GL, SMOOTH_EXP_INDBOX, SMOOTH_LOGEXP_INDBOX, SMOOTH_OSBA_L1L2, SMOOTH_OSBA_GL = range(7)
 METHOD_N, METHOD_GGN, METHOD_LQN = 0, 1, 2
 WEIGHTS_NEWTON, WEIGHTS_GGN = 0, 1
-STAGES = ("forward", "adjoint", "gram", "solve", "vector", "allreduce", "fused", "reserved")
+STAGES = ("forward", "adjoint", "gram", "solve", "vector", "allreduce", "fused", "gram_finalize")
 
 # every symbol include/scs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
