@@ -356,6 +356,11 @@ def main():
             hbm, peaks_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json"
         except Exception:
             pass
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}) if world == 1 and not args.rows else {}
+        except Exception:
+            pass
         g_ms, g_calls = stages["gram"]
         f_ms, f_calls = stages["forward"]
         a_ms, a_calls = stages["adjoint"]
@@ -365,7 +370,7 @@ def main():
             flops = float(nl) * m * (m + 1)
             ach = flops / (g_ms / g_calls * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "k_gram (DMMA.8x8x4 SYRK, TMA-fed)", "achieved": ach, "peak": peak_sus,
-                    "unit": "TFLOP/s", "frac": ach / peak_sus, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak_sus, "traffic": traffic.get("k_gram"),
                     "peak_source": "fp64 cuBLAS DGEMM 8192^3 via torch.matmul, sustained (back-to-back ~1.5 s), measured live "
                                    f"in this run; burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)",
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": g_ms / g_calls, "launches_timed": g_calls}
@@ -376,10 +381,10 @@ def main():
                 ach = by / (s_ms / s_calls * 1e-3) / 1e9
                 stream[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                               "algorithmic_bytes_per_launch": by, "ms_per_launch": s_ms / s_calls,
-                              "launches_timed": s_calls, "peak_source": peaks_src}
+                              "launches_timed": s_calls, "peak_source": peaks_src, "traffic": traffic.get("k_" + nm)}
         if roof is None and stream:  # LQN workloads: the streaming pass is the dominant kernel
             k = "forward" if "forward" in stream else "adjoint"
-            roof = dict(stream[k], kernel="k_" + k, traffic=None)
+            roof = dict(stream[k], kernel="k_" + k)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(cpu_sample_rows(wl), n_local)

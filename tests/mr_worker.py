@@ -1,0 +1,73 @@
+"""Worker for tests/test_gpu_multirank.py — launched by torch.distributed.run, one rank per GPU.  Each rank uploads
+its contiguous row block; results must match the full-batch oracle within the 1e-10 bar on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "selfconcordantsmoothoptimization.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+import scs_b200 as S  # noqa: E402
+from oracle import scs_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = S.context_from_env()
+    worst = 0.0
+    for name in ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1", "c4_ls_ggn_gl", "c5_ls_n_indbox"):
+        A, y, x0 = cases.data(name)
+        mo, modelo, reg, ho, kw = cases.build(name, O)
+        so = O.iterate(mo, modelo, reg, ho, **kw)
+        r0, nl = S.shard_rows(A.shape[0], world, rank)
+        # loss scale / denominator must stay the full-batch one: build with the full data for the constants,
+        # then hand this rank's rows to the GPU problem
+        mg, full_model_unused, reg, hg, kw = None, None, reg, None, kw
+        n = A.shape[0]
+        lib = S
+        if name == "c2_logreg_ggn_l1":
+            model = lib.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x0, lib.LogisticLoss(1 / n, "consistent"), 1e-2, ctx=ctx)
+            mg, hg = lib.ProxGGNSCORE(), lib.PHuberSmootherL1L2(1.0)
+        elif name == "c3_logreg_lqn_l1":
+            model = lib.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x0, lib.LogisticLoss(1 / n), 1e-2, ctx=ctx)
+            mg, hg = lib.ProxLQNSCORE(m=10), lib.PHuberSmootherL1L2(1.0)
+        elif name == "c4_ls_ggn_gl":
+            m = A.shape[1]
+            ng = m // 64
+            ind = np.array([[g * 64 + 1 for g in range(ng)], [(g + 1) * 64 for g in range(ng)], [1] * ng])
+            model = lib.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x0, lib.LeastSquaresLoss(n), [1e-8, 1e-2],
+                                P=lib.get_P(m, np.arange(1, m + 1), ind), ctx=ctx)
+            mg, hg = lib.ProxGGNSCORE(), lib.PHuberSmootherGL(1e-2, model)
+        else:
+            model = lib.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x0, lib.LeastSquaresLoss(n), 1e-4, C_set=(-0.5, 0.5), ctx=ctx)
+            mg, hg = lib.ProxNSCORE(), lib.PHuberSmootherIndBox(-0.5, 0.5, 0.6)
+        for dl in (False, True):
+            sg = S.iterate(mg, model, reg, hg, verbose=0, device_loop=dl, **kw)
+            ex = np.linalg.norm(sg.x - so.x) / np.linalg.norm(so.x)
+            eo = max(abs(a - b) / abs(b) for a, b in zip(sg.obj, so.obj) if np.isfinite(b))
+            assert sg.epochs == so.epochs, (name, sg.epochs, so.epochs)
+            assert ex <= 1e-10 and eo <= 1e-10, (name, rank, ex, eo)
+            assert np.array_equal(sg.x != 0, so.x != 0)
+            worst = max(worst, ex, eo)
+        # every rank must hold bitwise the same iterate (replicated x-update on identical all-reduced data)
+        t = torch.from_numpy(sg.x.copy()).cuda()
+        lst = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(lst, t)
+        assert all(torch.equal(lst[0], u) for u in lst), name
+        model.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIRANK_OK world={world} worst_rel_err={worst:.3e}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
