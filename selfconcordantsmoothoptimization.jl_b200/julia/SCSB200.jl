@@ -1,0 +1,210 @@
+# SCSB200.jl — Julia shim that routes the per-iteration hot path of SelfConcordantSmoothOptimization.jl
+# (ProxNSCORE / ProxGGNSCORE / ProxLQNSCORE) to libscs_b200.so through `ccall`.
+#
+# Drop-in: `Problem(A, y, x0, f, λ; ...)`, `iterate!(method, problem, reg_name, hμ; ...)` and the `Solution` fields
+# keep their reference meaning.  The only change a user makes is to pass one of the built-in loss objects
+# (`LogisticLoss`, `LeastSquaresLoss`, `QuadFormLoss`; all `<: Function`, so `Problem`'s `f::Function` signature,
+# src/problems.jl:65, accepts them).  An arbitrary closure `f` — which only ForwardDiff could differentiate — is
+# rejected with an error instead of silently running on the CPU.
+#
+# NOTE: no Julia binary exists in the build image, so this file has not been executed there.  It is kept 1:1 with
+# the Python ctypes mirror (scs_b200/api.py), which is what the test-suite drives; both bind the same C symbols
+# (include/scs_b200.h).
+module SCSB200
+
+using SelfConcordantSmoothOptimization
+import SelfConcordantSmoothOptimization: iterate!, ProximalMethod, ProxNSCORE, ProxGGNSCORE, ProxLQNSCORE,
+    Problem, Solution, PHuberSmootherL1L2, PHuberSmootherIndBox, PHuberSmootherGL, ExponentialSmootherIndBox,
+    LogExpSmootherIndBox, OsBaSmootherL1L2, OsBaSmootherGL, bounds_sanity_check
+using LinearAlgebra, Dates
+
+export LogisticLoss, LeastSquaresLoss, QuadFormLoss, GPUContext, gpu_iterate!
+
+const LIB = get(ENV, "SCS_B200_LIB", joinpath(@__DIR__, "..", "libscs_b200.so"))
+
+# ---- built-in losses: callable like the README closures, so the CPU reference can run the same object ----------
+struct LogisticLoss <: Function      # README.md:113,135-139 / test/test_algs.jl:9-11
+    scale::Float64
+    consistent_labels::Bool          # false: cross-entropy sees y as given (README feeds ±1); true: (y+1)/2
+end
+LogisticLoss(scale::Real) = LogisticLoss(Float64(scale), false)
+(L::LogisticLoss)(A, y, x) = L.scale * sum(log.(1 .+ exp.(-y .* (A * x))))
+function (L::LogisticLoss)(y, ŷ)
+    yc = L.consistent_labels ? (y .+ 1) ./ 2 : y
+    return -L.scale * sum(yc .* log.(ŷ) .+ (1 .- yc) .* log.(1 .- ŷ))
+end
+struct LeastSquaresLoss <: Function  # README.md:212-214,233-235
+    denom::Float64
+end
+(L::LeastSquaresLoss)(A, y, x) = 0.5 * sum((A * x .- y) .^ 2) / L.denom
+(L::LeastSquaresLoss)(y, ŷ) = 0.5 * sum((ŷ .- y) .^ 2) / L.denom
+struct QuadFormLoss <: Function      # test/test_algs.jl:90
+end
+(L::QuadFormLoss)(A, y, x) = 1 / 2 * (x' * (A * x)) + (y' * x)
+
+loss_code(L::LogisticLoss) = (Cint(0), L.scale, Cint(L.consistent_labels ? 1 : 0))
+loss_code(L::LeastSquaresLoss) = (Cint(1), L.denom, Cint(0))
+loss_code(L::QuadFormLoss) = (Cint(2), 0.0, Cint(0))
+loss_code(f) = Base.error("scs_b200: arbitrary user f (ForwardDiff-only path) is not supported on the GPU; " *
+                          "pass LogisticLoss / LeastSquaresLoss / QuadFormLoss")
+
+# ---- status handling: rethrow with Base.error so the user-visible failure class matches the reference -----------
+lasterr() = unsafe_string(ccall((:scs_last_error, LIB), Cstring, ()))
+check(code::Cint) = code == 0 ? nothing : Base.error("scs_b200 [$code]: " * lasterr())
+
+mutable struct GPUContext
+    h::Ptr{Cvoid}
+    function GPUContext(device::Integer=0; rank::Integer=0, world::Integer=1, unique_id::Vector{UInt8}=UInt8[])
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        idp = world > 1 ? pointer(unique_id) : Ptr{UInt8}(C_NULL)
+        GC.@preserve unique_id check(ccall((:scs_ctx_create, LIB), Cint, (Cint, Cint, Cint, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+                                           device, rank, world, idp, out))
+        c = new(out[])
+        finalizer(x -> ccall((:scs_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+function unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:scs_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+
+mutable struct GPUProblem
+    h::Ptr{Cvoid}
+    m::Int
+    ctx::GPUContext
+end
+
+# Upload model.A / model.y once (replaces the per-iteration `Matrix(As')` copy of iterate.jl:206-207).
+function GPUProblem(ctx::GPUContext, model)
+    code, param, lmode = loss_code(model.f)
+    any(x -> x !== nothing, (model.grad_fx, model.hess_fx, model.jac_yx, model.grad_fy, model.hess_fy)) &&
+        Base.error("scs_b200: user derivative closures cannot run on the GPU")
+    (model.out_fn !== nothing) && @info "out_fn is ignored: the built-in loss carries its own model output function"
+    A = Matrix{Float64}(model.A)
+    y = Vector{Float64}(vec(model.y))
+    n, m = size(A)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve A y check(ccall((:scs_problem_create, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
+        ctx.h, A, n, m, stride(A, 2), y, code, param, lmode, out))
+    p = GPUProblem(out[], m, ctx)
+    finalizer(x -> ccall((:scs_problem_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
+    return p
+end
+
+const REG = Dict("l1" => 0, "l2" => 1, "indbox" => 2, "gl" => 3)
+smoother_code(::PHuberSmootherL1L2) = 0
+smoother_code(::PHuberSmootherIndBox) = 1
+smoother_code(::PHuberSmootherGL) = 2
+smoother_code(::ExponentialSmootherIndBox) = 3
+smoother_code(::LogExpSmootherIndBox) = 4
+smoother_code(::OsBaSmootherL1L2) = 5
+smoother_code(::OsBaSmootherGL) = 6
+method_code(::ProxNSCORE) = 0
+method_code(::ProxGGNSCORE) = 1
+method_code(::ProxLQNSCORE) = 2
+
+function bounds_of(C_set)   # prox-operators.jl:36-45
+    if SelfConcordantSmoothOptimization.is_interval_set(C_set)
+        return isa(C_set, Tuple) ? ([minimum.(C_set)...], [maximum.(C_set)...]) : ([minimum(C_set)], [maximum(C_set)])
+    end
+    return (collect(Float64, C_set[1]), collect(Float64, C_set[2]))
+end
+
+# The IndBox smoothers close over their bounds; the shim needs them again for the device descriptor, so the caller
+# passes them through `smoother_bounds` (defaults to model.C_set, which is what README / tests use).
+function configure!(p::GPUProblem, method, model, reg_name::String, hμ; smoother_bounds=nothing)
+    haskey(REG, reg_name) || Base.error("reg_name not valid.")
+    λ = model.λ
+    lam1, lam2 = reg_name == "gl" ? (Float64(λ[1]), Float64(λ[2])) : (Float64(length(λ) > 1 ? λ[1] : λ), 0.0)
+    reg_name == "gl" && length(λ) != 2 &&
+        Base.error("Please provide a Tuple or Vector with exactly two entries for λ, e.g. [λ1, λ2]")
+    ind = reg_name == "gl" ? Matrix{Int64}(model.P.ind) : zeros(Int64, 3, 0)
+    perm = reg_name == "gl" ? Vector{Int64}(model.P.G) : Int64[]
+    lb, ub = reg_name == "indbox" ? bounds_of(model.C_set) : (Float64[], Float64[])
+    GC.@preserve ind perm lb ub check(ccall((:scs_set_regularizer, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Float64, Float64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+        p.h, REG[reg_name], lam1, lam2, isempty(ind) ? C_NULL : pointer(ind), size(ind, 2),
+        isempty(perm) ? C_NULL : pointer(perm), isempty(lb) ? C_NULL : pointer(lb), length(lb),
+        isempty(ub) ? C_NULL : pointer(ub), length(ub)))
+    slb, sub = smoother_bounds === nothing ? (lb, ub) : (collect(Float64, smoother_bounds[1]), collect(Float64, smoother_bounds[2]))
+    GC.@preserve slb sub check(ccall((:scs_set_smoother, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+        p.h, smoother_code(hμ), Float64(hμ.μ), isempty(slb) ? C_NULL : pointer(slb), length(slb),
+        isempty(sub) ? C_NULL : pointer(sub), length(sub)))
+    mem = method isa ProxLQNSCORE ? method.m : 10
+    check(ccall((:scs_set_method, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint),
+                p.h, method_code(method), method.ss_type, method.use_prox ? 1 : 0, mem))
+    check(ccall((:scs_set_L, LIB), Cint, (Ptr{Cvoid}, Cint, Float64), p.h, model.L === nothing ? 0 : 1,
+                model.L === nothing ? 0.0 : Float64(model.L)))
+end
+
+# model.f(model.A, model.y, x) and get_reg(model, x, reg_name)   — iterate.jl:189-190
+function gpu_objective(p::GPUProblem, x::Vector{Float64})
+    f = Ref{Float64}(0.0); r = Ref{Float64}(0.0)
+    GC.@preserve x check(ccall((:scs_objective, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ref{Float64}), p.h, x, f, r))
+    return f[], r[]
+end
+
+# step!(method, model, reg_name, hμ, As, x, x_prev, ys, Cmat, iter)   — iterate.jl:233
+function gpu_step(p::GPUProblem, x::Vector{Float64}, x_prev::Vector{Float64}, iter::Integer; return_dx=false)
+    x_new = Vector{Float64}(undef, p.m)
+    dx = return_dx ? Vector{Float64}(undef, p.m) : Float64[]
+    pri = Ref{Float64}(0.0)
+    GC.@preserve x x_prev x_new dx check(ccall((:scs_step, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+        p.h, x, x_prev, iter, x_new, return_dx ? pointer(dx) : C_NULL, pri))
+    return return_dx ? (x_new, dx, pri[]) : (x_new, pri[])
+end
+
+# optim_loop! (iterate.jl:100-266) with the two hot call sites routed to the GPU; histories, stopping rules and the
+# Solution are the reference's.  Full batch only (mini-batch options are rejected, not emulated on the CPU).
+function gpu_iterate!(method::ProximalMethod, model, reg_name, hμ; ctx::GPUContext=GPUContext(0), α=nothing,
+                      batch_size=nothing, slice_samples=false, max_epoch=1000, x_tol=1e-10, f_tol=1e-10,
+                      smoother_bounds=nothing, kwargs...)
+    (batch_size !== nothing || slice_samples) && Base.error("scs_b200: mini-batch / slice_samples are not supported on the GPU path")
+    SelfConcordantSmoothOptimization.set_name!(method, [])
+    α !== nothing && (model.L = 1 / α)
+    p = GPUProblem(ctx, model)
+    configure!(p, method, model, reg_name, hμ; smoother_bounds=smoother_bounds)
+    objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
+    x_star = model.x
+    fs, rs = gpu_objective(p, x_star)
+    obj_star = fs + rs
+    x = copy(model.x0); x_prev = deepcopy(x)
+    check(ccall((:scs_method_init, LIB), Cint, (Ptr{Cvoid},), p.h))
+    rel_err(v) = reg_name == "gl" ? sum(abs2, x_star - v) / length(v) : max(norm(v - x_star) / max(norm(x_star), 1), x_tol)
+    frel(o) = max(norm(o - obj_star) / norm(obj_star), f_tol)
+    pri = nothing; epochs = 0; f_rel_error = 0.0
+    t0 = now()
+    push_stat!(o, f, r, fr) = (push!(objs, o); push!(fvals, f); push!(pris, pri); push!(rels, r); push!(frels, fr);
+                               push!(times, (now() - t0).value / 1000))
+    for epoch_t in 1:max_epoch
+        f, r = gpu_objective(p, x); obj = f + r
+        f_rel_error = frel(obj)
+        push_stat!(obj, f, rel_err(x), f_rel_error)
+        if epoch_t == max_epoch
+            f, r = gpu_objective(p, x); obj = f + r; f_rel_error = frel(obj)
+            push_stat!(obj, f, rel_err(x), f_rel_error)
+        end
+        x_new, pri = gpu_step(p, x, x_prev, epoch_t)
+        if norm(x_new - x) < x_tol * max(norm(x), 1) || f_rel_error ≤ f_tol || pri < x_tol
+            if epoch_t != max_epoch
+                f, r = gpu_objective(p, x_new); obj = f + r; f_rel_error = frel(obj)
+                push_stat!(obj, f, rel_err(x_new), f_rel_error)
+            end
+            x_prev = deepcopy(x); x = x_new; epochs += 1
+        else
+            x_prev = deepcopy(x); x = x_new
+        end
+        if norm(x - x_prev) < x_tol * max(norm(x_prev), 1) || f_rel_error ≤ f_tol || pri < x_tol
+            break
+        end
+        epochs += 1
+    end
+    return Solution(x, objs, fvals, pris, [], rels, frels, Dict(), times, epochs, model)
+end
+
+end # module
