@@ -108,6 +108,11 @@ int scs_set_smoother(scs_problem* p, int smoother_kind, double mu, const double*
                      const double* ub, int64_t nub);
 int scs_set_method(scs_problem* p, int method_kind, int ss_type, int use_prox, int lbfgs_m);
 int scs_set_L(scs_problem* p, int has_L, double L);
+/* Gram kernel selection: 0 = auto (tcgen05 int8 emulated-fp64 path when the weights are non-negative and the shard
+ * is large, DMMA otherwise), 1 = always DMMA.8x8x4, 2 = tcgen05 int8 whenever the weights are non-negative.
+ * scs_get_gram_path reports what the last Gram used (1 = DMMA, 2 = tcgen05 int8). */
+int scs_set_gram_mode(scs_problem* p, int mode);
+int scs_get_gram_path(scs_problem* p, int* path);
 int scs_method_init(scs_problem* p);
 
 /* ---- the two call sites of optim_loop! ------------------------------------------------- */

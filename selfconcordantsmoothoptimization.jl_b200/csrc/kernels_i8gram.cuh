@@ -1,0 +1,452 @@
+// K2' — emulated-FP64 Gram on the 5th-generation tensor cores (tcgen05 int8, exact int32 accumulation in TMEM).
+//
+// fp64 has no tcgen05.mma kind, so  G = A' diag(w) A  (prox-GGN-SCORE.jl:129, prox-N-SCORE.jl:63) is evaluated
+// through exact integer arithmetic (Ozaki scheme II / CRT):
+//
+//   1. C = diag(sqrt(w)) A is brought to fixed point per column:  X_ij = rint(C_ij * 2^(b - e_j)),  |X| <= 2^b,
+//      2^e_j >= max_i |C_ij|  (bound: max sqrt(w) * colmax|A|).  Needs w >= 0 (Newton weights, consistent-label
+//      GGN weights, least squares); otherwise the caller stays on the DMMA kernel.
+//   2. k_residues writes, for each of kNMod pairwise-coprime moduli p_l <= 256, the symmetric residue plane
+//      x_l = X mod p_l as int8 (column-major, K = rows contiguous).
+//   3. k_i8syrk computes S_l = x_l' x_l mod p_l on lower-triangle 128x256 tiles with tcgen05.mma.kind::i8
+//      (TMA SWIZZLE_128B operand tiles -> 4-stage mbarrier ring -> UMMA 128x256x32, int32 accumulators in TMEM,
+//      double-buffered), one K chunk (<= 65536 rows: |acc| <= 2^30) at a time; the epilogue warps pull the
+//      accumulator with tcgen05.ld, reduce mod p_l and store int8 partial residues.
+//   4. k_crt sums the chunk residues, reconstructs R = sum_i X_ij X_ik exactly by CRT in 128-bit integers
+//      (P = prod p_l ~ 2^117.8 > 2 n 2^(2b)) and writes G_jk = R * 2^(e_j + e_k - 2b) to both triangles.
+//
+// The only rounding is the fixed-point quantisation of C (b = 48 bits below the column maximum at n = 1e6) and
+// the final conversion to fp64; the integer Gram itself is exact and bit-reproducible.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels_gram.cuh"  // mbarrier / TMA helpers, tri_decode
+
+namespace scs {
+
+#include "i8_moduli.inc"
+
+constexpr int kI8BM = 128;       // tile rows   (UMMA M)
+constexpr int kI8BN = 256;       // tile cols   (UMMA N)
+constexpr int kI8BK = 128;       // K bytes per stage = one 128-byte swizzle row = 4 UMMA k-steps of 32
+constexpr int kI8Stages = 4;
+constexpr int kI8ABytes = kI8BM * kI8BK;  // 16 KB
+constexpr int kI8BBytes = kI8BN * kI8BK;  // 32 KB
+constexpr int kI8StageBytes = kI8ABytes + kI8BBytes;
+constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 + 256;
+constexpr int kI8Threads = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kI8ChunkRows = 65536;       // 128*128*65536 = 2^30 < 2^31
+constexpr uint32_t kI8TmemCols = 512;     // two 256-column int32 accumulators
+constexpr int kI8Cluster = 4;             // CTAs per cluster: 4 vertically adjacent tiles, B slab multicast (64 rows each)
+constexpr int kI8BPart = kI8BN / kI8Cluster;  // rows of the B slab each CTA fetches and multicasts
+
+struct I8Plan {
+  int m;
+  int nmod;
+  int nchunks;
+  int ntiles;             // tile groups: kI8Cluster vertically adjacent 128x256 tiles that share one B slab
+  int64_t kblocks;        // ldx / 128
+  int64_t chunk_kblocks;  // kI8ChunkRows / 128
+  int64_t units;          // nmod * nchunks * ntiles
+  int ldp;                // bytes per row of a partial-residue matrix
+};
+
+// ---- column / row statistics -------------------------------------------------------------------------------
+// colmax[j] = max_i |A_ij|  (one pass over A, once per problem)
+__global__ void __launch_bounds__(256) k_colabsmax(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
+                                                   double* __restrict__ colmax) {
+  __shared__ double red[32];
+  const int j = blockIdx.x;
+  const double* col = A + (int64_t)j * ldd;
+  double v = 0.0;
+  for (int64_t i = threadIdx.x * 2; i < n; i += 512) {
+    const double2 a = ldg_stream2(col + i);
+    v = fmax(v, fmax(fabs(a.x), i + 1 < n ? fabs(a.y) : 0.0));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) v = fmax(v, red[q]);
+    colmax[j] = v;
+  }
+}
+// stat[0] = max_i w_i, stat[1] = min_i w_i   (single CTA)
+__global__ void __launch_bounds__(kVecThreads) k_wstat(const double* __restrict__ w, int64_t n,
+                                                       double* __restrict__ stat) {
+  __shared__ double smax[32], smin[32];
+  double mx = -1e300, mn = 1e300;
+  for (int64_t i = threadIdx.x; i < n; i += kVecThreads) {
+    const double v = w[i];
+    mx = fmax(mx, v);
+    mn = fmin(mn, v);
+    if (v != v) mn = -1.0;  // NaN weights: not eligible
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smax[threadIdx.x >> 5] = mx;
+    smin[threadIdx.x >> 5] = mn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < kVecThreads / 32; ++q) {
+      mx = fmax(mx, smax[q]);
+      mn = fmin(mn, smin[q]);
+    }
+    stat[0] = mx;
+    stat[1] = mn;
+  }
+}
+// e_j: smallest integer with sqrt(wmax)*colmax_j <= 2^e_j;  scale_j = 2^(b - e_j)
+__global__ void k_colscale(const double* __restrict__ colmax, const double* __restrict__ stat, int m, int b,
+                           int* __restrict__ ecol, double* __restrict__ scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double bound = sqrt(fmax(stat[0], 0.0)) * colmax[j];
+  int e = 0;
+  if (bound > 0.0) {
+    const double f = frexp(bound, &e);  // bound = f * 2^e, f in [0.5, 1)
+    (void)f;
+  } else {
+    e = -1000;  // all-zero column: any scale works, X = 0
+  }
+  ecol[j] = e;
+  scale[j] = bound > 0.0 ? ldexp(1.0, b - e) : 0.0;
+}
+
+// ---- residue planes ------------------------------------------------------------------------------------------
+// planes[l][i + j*ldx] = (rint(sqrt(w_i) * A_ij * scale_j)) mod p_l  (symmetric, int8).  Thread = 8 rows x 1 column.
+__global__ void __launch_bounds__(256)
+k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const double* __restrict__ w,
+           const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx) {
+  __shared__ double s_p[kNMod], s_ip[kNMod];
+  if (threadIdx.x < kNMod) {
+    s_p[threadIdx.x] = (double)c_mod_p[threadIdx.x];
+    s_ip[threadIdx.x] = 1.0 / (double)c_mod_p[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i0 >= ldd) return;  // ldd is a multiple of 16 and rows >= n hold zeros (w too)
+  double sw[8];
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    const double2 ww = *reinterpret_cast<const double2*>(w + i0 + q);
+    sw[q] = sqrt(ww.x);
+    sw[q + 1] = sqrt(ww.y);
+  }
+  const int64_t plane_stride = ldx * (int64_t)m;
+  for (int j = blockIdx.y; j < m; j += gridDim.y) {
+    const double sc = scale[j];
+    const double* col = A + (int64_t)j * ldd + i0;
+    double X[8];
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      const double2 a = ldg_stream2(col + q);
+      X[q] = rint((sw[q] * a.x) * sc);
+      X[q + 1] = rint((sw[q + 1] * a.y) * sc);
+    }
+    int8_t* dst = planes + (int64_t)j * ldx + i0;
+#pragma unroll
+    for (int l = 0; l < kNMod; ++l) {
+      const double p = s_p[l], ip = s_ip[l];
+      const int pi = c_mod_p[l];
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double qd = rint(X[q] * ip);
+        int r = (int)fma(-qd, p, X[q]);  // exact: |X|, |qd*p| < 2^52
+        if (2 * r >= pi) r -= pi;
+        if (2 * r < -pi) r += pi;
+        const uint32_t byte = (uint32_t)(r & 0xff);
+        if (q < 4)
+          lo |= byte << (8 * q);
+        else
+          hi |= byte << (8 * (q - 4));
+      }
+      *reinterpret_cast<uint2*>(dst + (int64_t)l * plane_stride) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// ---- tcgen05 helpers -------------------------------------------------------------------------------------------
+SCS_DEVINL void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+SCS_DEVINL void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+SCS_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SCS_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SCS_DEVINL void tc_commit_mc(uint64_t* bar, uint16_t mask) {  // arrive on the same barrier in every CTA of `mask`
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+SCS_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SCS_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+SCS_DEVINL void tc_commit(uint64_t* bar) {  // arrives on the mbarrier when all previously issued MMAs have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N = 256, K = 32
+SCS_DEVINL void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart (cute::UMMA::SmemDescriptor)
+SCS_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) /* LBO (unused for swizzled K-major) */ |
+         (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* descriptor version (sm_100) */ |
+         (2ull << 61) /* SWIZZLE_128B */;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = INT8, both K-major, N = 256, M = 128
+constexpr uint32_t kI8Idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kI8BN >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+
+SCS_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// unit -> (modulus l, chunk c, tile t): all tiles of one (l, c) are adjacent so concurrently running CTAs stream the
+// same rows of the same plane and share operand panels through L2
+SCS_DEVINL void i8_unit(const I8Plan& pl, int64_t u, int& l, int& c, int& t) {
+  t = (int)(u % pl.ntiles);
+  const int64_t lc = u / pl.ntiles;
+  c = (int)(lc % pl.nchunks);
+  l = (int)(lc / pl.nchunks);
+}
+
+// Launched as clusters of kI8Cluster CTAs.  CTA rank r of a cluster owns tile (tiles[t].x * kI8Cluster + r, tiles[t].y);
+// it fetches its own A slab and rows [r*kI8BPart, (r+1)*kI8BPart) of the shared B slab, multicast to the whole cluster.
+__global__ void __launch_bounds__(kI8Threads, 1)
+k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap bmap, I8Plan pl,
+         const int2* __restrict__ tiles, int8_t* __restrict__ partial /* [nmod][nchunks][m][ldp] */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = (uint64_t*)(smem + kI8Stages * kI8StageBytes);
+  uint64_t* empty = full + kI8Stages;
+  uint64_t* acc_full = empty + kI8Stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int64_t cid = blockIdx.x / kI8Cluster, ncl = gridDim.x / kI8Cluster;
+  constexpr uint16_t kMask = (uint16_t)((1u << kI8Cluster) - 1u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kI8Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kI8Cluster);  // one tcgen05.commit arrival from every CTA of the cluster
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kI8TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = cid; u < pl.units; u += ncl) {
+        int l, c, t;
+        i8_unit(pl, u, l, c, t);
+        const int2 tile = tiles[t];
+        const int64_t kb0 = (int64_t)c * pl.chunk_kblocks;
+        const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);  // all CTAs of the cluster have consumed this slot
+          mbar_expect_tx(&full[stage], kI8StageBytes);
+          uint8_t* sa = smem + stage * kI8StageBytes;
+          tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
+          tma_load_3d_mc(sa + kI8ABytes + crank * (kI8BPart * kI8BK), &bmap, &full[stage], (int)(kb * kI8BK),
+                         tile.y * kI8BN + crank * kI8BPart, l, kMask);
+          if (++stage == kI8Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int64_t u = cid; u < pl.units; u += ncl) {
+        int l, c, t;
+        i8_unit(pl, u, l, c, t);
+        const int64_t kb0 = (int64_t)c * pl.chunk_kblocks;
+        const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
+        mbar_wait(&acc_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * kI8BN);
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kI8StageBytes);
+          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kI8ABytes);
+#pragma unroll
+          for (int k = 0; k < kI8BK / 32; ++k)
+            umma_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kI8Idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          tc_commit_mc(&empty[stage], kMask);  // tells every producer of the cluster that this CTA is done with the slot
+          if (++stage == kI8Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&acc_full[as]);  // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> mod p -> int8 partial residues =====
+    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are accessible to this warp
+    const int row_in_tile = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t u = cid; u < pl.units; u += ncl) {
+      int l, c, t;
+      i8_unit(pl, u, l, c, t);
+      const int2 tile = tiles[t];
+      const int p = c_mod_p[l];
+      const double pd = (double)p, ip = 1.0 / pd;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const int jc = (tile.x * kI8Cluster + crank) * kI8BM + row_in_tile;
+      int8_t* prow = partial + (((int64_t)l * pl.nchunks + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
+      const uint32_t taddr = tmem_base + (uint32_t)(as * kI8BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < kI8BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+        uint32_t packed[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int bq = 0; bq < 4; ++bq) {
+            const double dv = (double)(int)v[4 * q + bq];
+            int r = (int)fma(-rint(dv * ip), pd, dv);
+            if (2 * r >= p) r -= p;
+            if (2 * r < -p) r += p;
+            word |= (uint32_t)(r & 0xff) << (8 * bq);
+          }
+          packed[q] = word;
+        }
+        const int kc0 = tile.y * kI8BN + cc * 32;
+        if (jc < pl.m && kc0 < pl.ldp) {
+          uint4* d4 = reinterpret_cast<uint4*>(prow + cc * 32);
+          d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (kc0 + 16 < pl.ldp) d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kI8TmemCols) : "memory");
+  }
+}
+
+// ---- CRT reconstruction -----------------------------------------------------------------------------------------
+// For each lower-triangle (jc >= kc): R = CRT({sum_c partial[l][c][jc][kc] mod p_l}) in (-P/2, P/2), then
+// G[jc,kc] = G[kc,jc] = R * 2^(e_jc + e_kc - 2b).
+__global__ void __launch_bounds__(256)
+k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ ecol, int b, double* __restrict__ G) {
+  const int kc = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int jc = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (jc >= pl.m || kc >= pl.m || kc > jc) return;
+  const int64_t cstride = (int64_t)pl.m * pl.ldp;
+  unsigned __int128 acc = 0;
+  double frac = 0.0;
+#pragma unroll 1
+  for (int l = 0; l < kNMod; ++l) {
+    const int p = c_mod_p[l];
+    const int8_t* src = partial + ((int64_t)l * pl.nchunks * pl.m + jc) * pl.ldp + kc;
+    int s = 0;
+    for (int c = 0; c < pl.nchunks; ++c) s += (int)src[c * cstride];
+    s %= p;
+    if (s < 0) s += p;
+    const unsigned tl = (unsigned)((s * c_mod_q[l]) % p);
+    const unsigned __int128 Ml = ((unsigned __int128)c_mod_Mhi[l] << 64) | c_mod_Mlo[l];
+    acc += Ml * tl;
+    frac += (double)tl / (double)p;
+  }
+  const unsigned __int128 P = ((unsigned __int128)c_P_hi << 64) | c_P_lo;
+  long long k = (long long)floor(frac);
+  if (k < 0) k = 0;
+  __int128 r = (__int128)acc - (__int128)(P * (unsigned __int128)k);
+  while (r < 0) r += (__int128)P;
+  while (r >= (__int128)P) r -= (__int128)P;
+  if (r > (__int128)(P >> 1)) r -= (__int128)P;
+  const bool neg = r < 0;
+  const unsigned __int128 mag = neg ? (unsigned __int128)(-r) : (unsigned __int128)r;
+  double d = ldexp((double)(unsigned long long)(mag >> 64), 64) + (double)(unsigned long long)mag;
+  if (neg) d = -d;
+  const int ej = ecol[jc], ek = ecol[kc];
+  const double g = (ej < -900 || ek < -900) ? 0.0 : ldexp(d, ej + ek - 2 * b);
+  G[(int64_t)kc * pl.m + jc] = g;
+  G[(int64_t)jc * pl.m + kc] = g;
+}
+
+}  // namespace scs

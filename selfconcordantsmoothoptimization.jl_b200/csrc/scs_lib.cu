@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels_gram.cuh"
+#include "kernels_i8gram.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_vec.cuh"
@@ -179,6 +180,18 @@ struct scs_problem {
   int ldp = 0;
   CUtensorMap amap{};
   bool gram_ready = false;
+  // emulated-fp64 Gram on tcgen05 int8 (kernels_i8gram.cuh)
+  int gram_mode = 0;   // 0 auto, 1 DMMA, 2 tcgen05 int8 when eligible (w >= 0), else DMMA
+  int last_gram_path = 0;  // 1 DMMA, 2 int8
+  bool i8_ready = false, i8_failed = false, i8_planes_valid = false;
+  int8_t *d_planes = nullptr, *d_i8partial = nullptr;
+  double *d_colmax = nullptr, *d_wstat = nullptr, *d_colscale = nullptr;
+  int* d_ecol = nullptr;
+  int2* d_i8tiles = nullptr;
+  int64_t ldx = 0;
+  int i8_b = 0, i8_clusters = 0;
+  I8Plan i8plan{};
+  CUtensorMap xmap{}, xmap_b{};
   // l-bfgs
   double *d_S = nullptr, *d_Y = nullptr;
   int64_t* d_state = nullptr;
@@ -355,6 +368,129 @@ static int gram_setup(scs_problem* p) {
   return SCS_OK;
 }
 
+
+// ---- emulated-fp64 Gram (tcgen05 int8 + CRT) ----------------------------------------------------------------
+static int i8_setup(scs_problem* p) {
+  if (p->i8_ready) return SCS_OK;
+  scs_ctx* c = p->ctx;
+  const int64_t m = p->m;
+  p->ldx = round_up(p->ldd, kI8BK);
+  const size_t plane_bytes = (size_t)kNMod * p->ldx * m;
+  I8Plan& pl = p->i8plan;
+  pl.m = (int)m;
+  pl.nmod = kNMod;
+  pl.kblocks = p->ldx / kI8BK;
+  pl.chunk_kblocks = kI8ChunkRows / kI8BK;
+  pl.nchunks = (int)((pl.kblocks + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
+  pl.ldp = (int)round_up(m, 16);
+  // tile groups (g, bj): rows [g*C*128, (g+1)*C*128) x columns [bj*256, +256) that touch the lower triangle
+  std::vector<int2> tiles;
+  const int nbi = (int)((m + kI8BM - 1) / kI8BM), nbj = (int)((m + kI8BN - 1) / kI8BN);
+  const int ngrp = (nbi + kI8Cluster - 1) / kI8Cluster;
+  for (int g = 0; g < ngrp; ++g)
+    for (int bj = 0; bj < nbj; ++bj)
+      if ((int64_t)bj * kI8BN <= (int64_t)(g + 1) * kI8Cluster * kI8BM - 1) tiles.push_back(make_int2(g, bj));
+  pl.ntiles = (int)tiles.size();
+  pl.units = (int64_t)pl.nmod * pl.nchunks * pl.ntiles;
+  const size_t partial_bytes = (size_t)kNMod * pl.nchunks * m * pl.ldp;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (plane_bytes + partial_bytes + (2ull << 30) > free_b) {
+    p->i8_failed = true;
+    return fail(SCS_OOM, "not enough HBM for the int8 residue planes");
+  }
+  CU_TRY(cudaMalloc((void**)&p->d_planes, plane_bytes));
+  CU_TRY(cudaMemsetAsync(p->d_planes, 0, plane_bytes, c->stream));
+  CU_TRY(cudaMalloc((void**)&p->d_i8partial, partial_bytes));
+  CU_TRY(cudaMemsetAsync(p->d_i8partial, 0, partial_bytes, c->stream));
+  SCS_TRY(dalloc(&p->d_colmax, m));
+  SCS_TRY(dalloc(&p->d_wstat, 4));
+  SCS_TRY(dalloc(&p->d_colscale, m));
+  CU_TRY(cudaMalloc((void**)&p->d_ecol, m * sizeof(int)));
+  CU_TRY(cudaMalloc((void**)&p->d_i8tiles, tiles.size() * sizeof(int2)));
+  CU_TRY(cudaMemcpyAsync(p->d_i8tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  // P/2 > n * 2^(2b)
+  int b = (int)std::floor((kLog2P - 1.0 - std::log2((double)p->ldx)) / 2.0);
+  p->i8_b = std::min(b, 50);
+  if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {(cuuint64_t)p->ldx, (cuuint64_t)m, (cuuint64_t)kNMod};
+  cuuint64_t gstride[2] = {(cuuint64_t)p->ldx, (cuuint64_t)p->ldx * (cuuint64_t)m};
+  cuuint32_t box[3] = {(cuuint32_t)kI8BK, 128u, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(&p->xmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, p->d_planes, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (int8 planes) failed: " + std::to_string((int)r));
+  cuuint32_t boxb[3] = {(cuuint32_t)kI8BK, (cuuint32_t)kI8BPart, 1u};
+  r = c->encode(&p->xmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, p->d_planes, gdim, gstride, boxb, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (int8 B slab) failed: " + std::to_string((int)r));
+  CU_TRY(cudaFuncSetAttribute(k_i8syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes));
+  {
+    StageTimer t(c, ST_FWD);
+    LAUNCH(c, k_colabsmax, (unsigned)m, 256, 0, p->dA, p->ldd, p->n, (int)m, p->d_colmax);
+  }
+  p->i8_ready = true;
+  return SCS_OK;
+}
+
+// returns *done = 0 when the weights are not eligible (negative / NaN): the caller then runs the DMMA kernel
+static int run_gram_i8(scs_problem* p, int* done) {
+  scs_ctx* c = p->ctx;
+  *done = 0;
+  SCS_TRY(i8_setup(p));
+  const int m = (int)p->m;
+  const bool const_w = p->loss.kind == SCS_LOSS_LEASTSQUARES;  // w = 1/denominator: planes never change
+  if (!(const_w && p->i8_planes_valid)) {
+    StageTimer t(c, ST_FUSED);
+    LAUNCH(c, k_wstat, 1, kVecThreads, 0, p->dw, p->n, p->d_wstat);
+    double st[2];
+    CU_TRY(cudaMemcpyAsync(st, p->d_wstat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (!(st[1] >= 0.0) || !std::isfinite(st[0])) return SCS_OK;  // not eligible
+    LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, p->d_colmax, p->d_wstat, m, p->i8_b, p->d_ecol, p->d_colscale);
+    const unsigned gx = (unsigned)((p->ldd / 8 + 255) / 256);
+    LAUNCH(c, k_residues, dim3(gx, (unsigned)std::min(m, 64)), 256, 0, p->dA, p->ldd, p->n, m, p->dw, p->d_colscale,
+           p->d_planes, p->ldx);
+    p->i8_planes_valid = true;
+  }
+  {
+    StageTimer t(c, ST_GRAM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(c->num_sms / kI8Cluster * kI8Cluster));
+    cfg.blockDim = dim3(kI8Threads);
+    cfg.dynamicSmemBytes = kI8SmemBytes;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kI8Cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent kernel: exactly as many clusters as can be co-resident (GPC shapes strand some SMs for clusters of 4)
+    if (p->i8_clusters == 0) {
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg) != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
+      p->i8_clusters = nc;
+    }
+    const int ncl = (int)std::min<int64_t>(p->i8_clusters, p->i8plan.units);
+    cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
+    cudaError_t le = cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, p->i8plan, (const int2*)p->d_i8tiles,
+                                        p->d_i8partial);
+    c->launches += 1;
+    if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
+  }
+  {
+    StageTimer t(c, ST_GRAMFIN);
+    LAUNCH(c, k_crt, dim3((m + 63) / 64, (m + 3) / 4), 256, 0, p->d_i8partial, p->i8plan, p->d_ecol, p->i8_b, p->d_G);
+  }
+  *done = 1;
+  return SCS_OK;
+}
+
 // G = A' diag(w) A (all-reduced, both triangles) into d_G, using the weights currently in d_w
 static int run_gram(scs_problem* p, XRef x) {
   scs_ctx* c = p->ctx;
@@ -365,6 +501,18 @@ static int run_gram(scs_problem* p, XRef x) {
     LAUNCH(c, k_quadform_hess, dim3((m + 255) / 256, m), 256, 0, p->dA, p->ldd, m, p->d_G);
     return SCS_OK;
   }
+  bool want_i8 = p->gram_mode == 2 || (p->gram_mode == 0 && p->m >= 512 && p->n >= 32768);
+  if (want_i8 && !p->i8_failed) {
+    int done = 0;
+    int rc = run_gram_i8(p, &done);
+    if (rc != SCS_OK && !(rc == SCS_OOM && p->gram_mode == 0)) return rc;
+    if (done) {
+      p->last_gram_path = 2;
+      SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
+      return SCS_OK;
+    }
+  }
+  p->last_gram_path = 1;
   {
     StageTimer t(c, ST_GRAM);
     const int grid = (int)std::min<int64_t>(c->num_sms, p->plan.units);
@@ -598,7 +746,8 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gq,    p->d_gqprev, p->d_gamma, p->d_q,   p->d_t1,     p->d_t2,    p->d_xstar,  p->d_trial,
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
-                  p->d_cdiag, p->d_ind,   p->d_perm};
+                  p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
+                  p->d_colscale, p->d_ecol, p->d_i8tiles};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
@@ -827,6 +976,18 @@ extern "C" int scs_set_L(scs_problem* p, int has_L, double L) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   p->has_L = has_L != 0;
   p->L = L;
+  return SCS_OK;
+}
+
+extern "C" int scs_set_gram_mode(scs_problem* p, int mode) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (mode < 0 || mode > 2) return fail(SCS_INVALID_ARG, "gram mode must be 0 (auto), 1 (DMMA) or 2 (tcgen05 int8)");
+  p->gram_mode = mode;
+  return SCS_OK;
+}
+extern "C" int scs_get_gram_path(scs_problem* p, int* path) {
+  if (!p || !path) return fail(SCS_INVALID_ARG, "NULL argument");
+  *path = p->last_gram_path;
   return SCS_OK;
 }
 

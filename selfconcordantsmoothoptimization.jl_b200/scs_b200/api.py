@@ -302,6 +302,15 @@ class Problem:
         K.check(K.lib().scs_prox(self._h, K.dptr(K.vec(u, self.m)), K.dptr(K.vec(hr, self.m)), float(ss), K.dptr(out)))
         return out
 
+    def set_gram_mode(self, mode):
+        """"auto" | "dmma" | "i8": which Gram kernel builds A'diag(w)A (the int8 tcgen05 path needs w >= 0)."""
+        K.check(K.lib().scs_set_gram_mode(self._h, {"auto": 0, "dmma": 1, "i8": 2}[mode]))
+
+    def gram_path(self):
+        v = C.c_int()
+        K.check(K.lib().scs_get_gram_path(self._h, C.byref(v)))
+        return {0: None, 1: "dmma", 2: "i8"}[v.value]
+
     def reg_value(self, x):
         v = C.c_double()
         K.check(K.lib().scs_reg_value(self._h, K.dptr(K.vec(x, self.m)), C.byref(v)))

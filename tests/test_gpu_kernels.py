@@ -210,3 +210,50 @@ def test_synthetic_generator_bits(scs):
         else:
             np.testing.assert_allclose(yg, synth.make_targets_ls(z, seed=1236, row0=row0), rtol=1e-12, atol=1e-14)
         p.close()
+
+
+# ---- emulated-fp64 Gram on tcgen05 int8 (kernels_i8gram.cuh) ------------------------------------------------
+@pytest.mark.parametrize("n,m", [(5, 2), (100, 50), (513, 130), (3001, 257), (4096, 512), (70001, 300), (131072 + 77, 640)])
+def test_gram_i8_matches_fp64(scs, n, m):
+    """Forced int8/CRT path vs the fp64 oracle Gram.  The integer Gram is exact; the only error is the fixed-point
+    quantisation of sqrt(w)*A (>= 48 bits below the column maximum), so entries agree to ~1e-13 of the diagonal scale.
+    n > 65536 exercises several K chunks, m not a multiple of 128/256 the ragged tiles."""
+    A, y, x = logistic_problem(n, m)
+    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "consistent"), 0.1)
+    p.set_gram_mode("i8")
+    Lo = O.LogisticLoss(1 / n, "consistent")
+    z = A @ x
+    for wk in ("newton", "ggn"):
+        w = Lo.hess_weights(z, y) if wk == "newton" else Lo.ggn_weights(z, y)[1]
+        G = p.gram(x, weights=wk)
+        assert p.gram_path() == "i8"
+        Gref = A.T @ (w[:, None] * A)
+        assert np.array_equal(G, G.T)
+        d = np.sqrt(np.diag(Gref))
+        assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 2e-12
+    # negative weights (literal +-1 labels, GGN): not eligible -> the DMMA kernel must take over
+    p2 = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "literal"), 0.1)
+    p2.set_gram_mode("i8")
+    G2 = p2.gram(x, weights="ggn")
+    w2 = O.LogisticLoss(1 / n).ggn_weights(z, y)[1]
+    if np.any(w2 < 0):
+        assert p2.gram_path() == "dmma"
+    assert np.max(np.abs(G2 - A.T @ (w2[:, None] * A))) <= 1e-12 * np.max(np.abs(G2))
+    p.close()
+    p2.close()
+
+
+def test_gram_i8_vs_dmma_bitwise_reproducible(scs):
+    n, m = 40000, 384
+    A, y, x = logistic_problem(n, m)
+    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "consistent"), 0.1)
+    p.set_gram_mode("i8")
+    G1 = p.gram(x, weights="ggn")
+    G2 = p.gram(x * 1.0000001, weights="ggn")
+    G3 = p.gram(x, weights="ggn")
+    assert np.array_equal(G1, G3) and not np.array_equal(G1, G2)
+    p.set_gram_mode("dmma")
+    Gd = p.gram(x, weights="ggn")
+    d = np.sqrt(np.diag(Gd))
+    assert np.max(np.abs(G1 - Gd) / np.outer(d, d)) <= 2e-12
+    p.close()

@@ -151,3 +151,20 @@ def test_error_behaviour(scs):
         pw = scs.Problem(A[:10], y[:10], x0, scs.LogisticLoss(1 / 50), 0.1)
         scs.iterate(scs.ProxGGNSCORE(), pw, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0)
     p.close()
+
+
+@pytest.mark.parametrize("name", ["c2_logreg_ggn_l1", "c4_ls_ggn_gl", "c5_ls_n_indbox", "c1_readme_logreg_n"])
+def test_config_parity_i8_gram(scs, name):
+    """Same 1e-10 bar with the Gram built by the tcgen05 int8 / CRT kernel (forced; auto picks it only for big shards)."""
+    mo, modelo, reg, ho, kw = cases.build(name, O)
+    so = O.iterate(mo, modelo, reg, ho, **kw)
+    mg, modelg, reg, hg, kw = cases.build(name, scs)
+    modelg.set_gram_mode("i8")
+    sg = scs.iterate(mg, modelg, reg, hg, verbose=0, device_loop=True, **kw)
+    assert modelg.gram_path() == "i8"
+    assert sg.epochs == so.epochs
+    assert relerr(sg.x, so.x) <= TOL, relerr(sg.x, so.x)
+    assert hist_err(sg.obj, so.obj) <= TOL
+    if reg in ("l1", "gl"):
+        assert np.array_equal(sg.x != 0, so.x != 0)
+    modelg.close()
