@@ -246,6 +246,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override n (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gram", default="auto", choices=["auto", "dmma", "i8"], help="Gram kernel selection")
+    ap.add_argument("--no-peak", action="store_true", help="skip the live DGEMM peak measurement (profiling runs)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.rows:
@@ -280,9 +282,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    peak_burst, peak_sus = fp64_peak_tflops(torch, dev)
+    peak_burst, peak_sus = (35.4, 35.4) if args.no_peak else fp64_peak_tflops(torch, dev)
     t_up0 = time.perf_counter()
     method, model, reg, hmu, alpha = build_problem(S, wl, n, row0, n_local, ctx, x0)
+    model.set_gram_mode(args.gram)
     ctx.sync()
     t_gen = time.perf_counter() - t_up0
     ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
@@ -366,7 +369,29 @@ def main():
         a_ms, a_calls = stages["adjoint"]
         nl = n_local
         roof = None
-        if g_calls:
+        gram_path = model.gram_path()
+        gram_equiv = None
+        if g_calls and gram_path == "i8":
+            # emulated-fp64 Gram: k_i8syrk runs NMOD int8 SYRKs; algorithmic int8 ops = NMOD * n*m*(m+1)
+            nmod = 15
+            ops = nmod * float(nl) * m * (m + 1)
+            ach = ops / (g_ms / g_calls * 1e-3) / 1e12
+            try:
+                bf16_sus = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+                i8_peak, i8_src = 2.0 * bf16_sus, ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 tcgen05 issues at twice "
+                                                   "the bf16 rate; no int8 figure is measured by the driver)")
+            except Exception:
+                i8_peak, i8_src = 2.0 * 1400.0, "2 x 1.4 PFLOP/s sustained bf16 fallback of B200_PROFILING.md"
+            roof = {"bound": "tensor", "kernel": "k_i8syrk (tcgen05.mma kind::i8, TMA multicast, TMEM int32 accumulators)",
+                    "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": traffic.get("k_i8syrk"),
+                    "peak_source": i8_src, "algorithmic_ops_per_launch": ops, "ms_per_launch": g_ms / g_calls,
+                    "launches_timed": g_calls}
+            tot = (g_ms + stages["fused"][0] + stages["gram_finalize"][0]) / g_calls
+            fe = float(nl) * m * (m + 1) / (tot * 1e-3) / 1e12
+            gram_equiv = {"what": "whole emulated-fp64 Gram (residues + int8 SYRK + CRT) as fp64-equivalent throughput",
+                          "fp64_equiv_tflops": fe, "ms": tot, "vs_measured_dgemm_peak": fe / peak_sus,
+                          "dgemm_peak_tflops": peak_sus}
+        elif g_calls:
             flops = float(nl) * m * (m + 1)
             ach = flops / (g_ms / g_calls * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "k_gram (DMMA.8x8x4 SYRK, TMA-fed)", "achieved": ach, "peak": peak_sus,
@@ -404,7 +429,8 @@ def main():
                         "ms_per_step": 1e3 * t_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_stream": stream,
                 "stages_ms_per_step": {k: v[0] / K for k, v in stages.items() if v[1]},
-                "cpu_baseline": cpu, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sus}}
+                "cpu_baseline": cpu, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sus},
+                "gram_path": gram_path, "gram_fp64_equivalent": gram_equiv}
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:

@@ -121,6 +121,12 @@ __global__ void k_colscale(const double* __restrict__ colmax, const double* __re
 
 // ---- residue planes ------------------------------------------------------------------------------------------
 // planes[l][i + j*ldx] = (rint(sqrt(w_i) * A_ij * scale_j)) mod p_l  (symmetric, int8).  Thread = 8 rows x 1 column.
+// All roundings / conversions use the 1.5*2^52 magic constant (DADD/DFMA only, no XU-pipe conversions):
+//   X  = (v + M) - M                      v rounded to the nearest integer, |X| <= 2^50
+//   q  = fma(X, 1/p, M) - M               nearest integer to X/p (off by at most one, only next to a half-way point)
+//   r  = fma(-q, p, X)                    exact, |r| <= p/2 (+1 for p = 256 at a tie) -> its low byte is a valid residue
+//   lo32(r + M)                           two's-complement bits of r
+constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 __global__ void __launch_bounds__(256)
 k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const double* __restrict__ w,
            const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx) {
@@ -147,27 +153,23 @@ k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const do
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
       const double2 a = ldg_stream2(col + q);
-      X[q] = rint((sw[q] * a.x) * sc);
-      X[q + 1] = rint((sw[q + 1] * a.y) * sc);
+      X[q] = ((sw[q] * a.x) * sc) + kMagic;  // kept biased: XM = X + M (exact, |X| <= 2^50)
+      X[q + 1] = ((sw[q + 1] * a.y) * sc) + kMagic;
     }
     int8_t* dst = planes + (int64_t)j * ldx + i0;
 #pragma unroll
     for (int l = 0; l < kNMod; ++l) {
       const double p = s_p[l], ip = s_ip[l];
-      const int pi = c_mod_p[l];
-      uint32_t lo = 0, hi = 0;
+      uint32_t b[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const double qd = rint(X[q] * ip);
-        int r = (int)fma(-qd, p, X[q]);  // exact: |X|, |qd*p| < 2^52
-        if (2 * r >= pi) r -= pi;
-        if (2 * r < -pi) r += pi;
-        const uint32_t byte = (uint32_t)(r & 0xff);
-        if (q < 4)
-          lo |= byte << (8 * q);
-        else
-          hi |= byte << (8 * (q - 4));
+        const double x = X[q] - kMagic;
+        const double qd = fma(x, ip, kMagic) - kMagic;
+        b[q] = (uint32_t)__double2loint(fma(-qd, p, X[q]));  // = M + r exactly; the low word holds r
       }
+      // gather the low bytes of eight words into two
+      const uint32_t lo = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+      const uint32_t hi = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
       *reinterpret_cast<uint2*>(dst + (int64_t)l * plane_stride) = make_uint2(lo, hi);
     }
   }
@@ -410,43 +412,60 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
 
 // ---- CRT reconstruction -----------------------------------------------------------------------------------------
 // For each lower-triangle (jc >= kc): R = CRT({sum_c partial[l][c][jc][kc] mod p_l}) in (-P/2, P/2), then
-// G[jc,kc] = G[kc,jc] = R * 2^(e_jc + e_kc - 2b).
+// G[jc,kc] = G[kc,jc] = R * 2^(e_jc + e_kc - 2b).  One thread reconstructs 4 consecutive kc (32-bit loads of the
+// int8 partial residues).
 __global__ void __launch_bounds__(256)
 k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ ecol, int b, double* __restrict__ G) {
-  const int kc = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int kc0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
   const int jc = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (jc >= pl.m || kc >= pl.m || kc > jc) return;
+  if (jc >= pl.m || kc0 >= pl.m || kc0 > jc) return;
   const int64_t cstride = (int64_t)pl.m * pl.ldp;
-  unsigned __int128 acc = 0;
-  double frac = 0.0;
+  unsigned __int128 acc[4] = {0, 0, 0, 0};
+  double frac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
   for (int l = 0; l < kNMod; ++l) {
-    const int p = c_mod_p[l];
-    const int8_t* src = partial + ((int64_t)l * pl.nchunks * pl.m + jc) * pl.ldp + kc;
-    int s = 0;
-    for (int c = 0; c < pl.nchunks; ++c) s += (int)src[c * cstride];
-    s %= p;
-    if (s < 0) s += p;
-    const unsigned tl = (unsigned)((s * c_mod_q[l]) % p);
+    const int p = c_mod_p[l], ql = c_mod_q[l];
+    const int8_t* src = partial + ((int64_t)l * pl.nchunks * pl.m + jc) * pl.ldp + kc0;
+    int s[4] = {0, 0, 0, 0};
+    for (int c = 0; c < pl.nchunks; ++c) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(src + c * cstride);
+      s[0] += (int)(int8_t)(v & 0xff);
+      s[1] += (int)(int8_t)((v >> 8) & 0xff);
+      s[2] += (int)(int8_t)((v >> 16) & 0xff);
+      s[3] += (int)(int8_t)(v >> 24);
+    }
     const unsigned __int128 Ml = ((unsigned __int128)c_mod_Mhi[l] << 64) | c_mod_Mlo[l];
-    acc += Ml * tl;
-    frac += (double)tl / (double)p;
+    const double ipd = 1.0 / (double)p;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int r = s[e] % p;
+      if (r < 0) r += p;
+      const unsigned tl = (unsigned)((r * ql) % p);
+      acc[e] += Ml * tl;
+      frac[e] += (double)tl * ipd;
+    }
   }
   const unsigned __int128 P = ((unsigned __int128)c_P_hi << 64) | c_P_lo;
-  long long k = (long long)floor(frac);
-  if (k < 0) k = 0;
-  __int128 r = (__int128)acc - (__int128)(P * (unsigned __int128)k);
-  while (r < 0) r += (__int128)P;
-  while (r >= (__int128)P) r -= (__int128)P;
-  if (r > (__int128)(P >> 1)) r -= (__int128)P;
-  const bool neg = r < 0;
-  const unsigned __int128 mag = neg ? (unsigned __int128)(-r) : (unsigned __int128)r;
-  double d = ldexp((double)(unsigned long long)(mag >> 64), 64) + (double)(unsigned long long)mag;
-  if (neg) d = -d;
-  const int ej = ecol[jc], ek = ecol[kc];
-  const double g = (ej < -900 || ek < -900) ? 0.0 : ldexp(d, ej + ek - 2 * b);
-  G[(int64_t)kc * pl.m + jc] = g;
-  G[(int64_t)jc * pl.m + kc] = g;
+  const int ej = ecol[jc];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int kc = kc0 + e;
+    if (kc >= pl.m || kc > jc) continue;
+    long long k = (long long)floor(frac[e]);
+    if (k < 0) k = 0;
+    __int128 r = (__int128)acc[e] - (__int128)(P * (unsigned __int128)k);
+    while (r < 0) r += (__int128)P;
+    while (r >= (__int128)P) r -= (__int128)P;
+    if (r > (__int128)(P >> 1)) r -= (__int128)P;
+    const bool neg = r < 0;
+    const unsigned __int128 mag = neg ? (unsigned __int128)(-r) : (unsigned __int128)r;
+    double d = ldexp((double)(unsigned long long)(mag >> 64), 64) + (double)(unsigned long long)mag;
+    if (neg) d = -d;
+    const int ek = ecol[kc];
+    const double g = (ej < -900 || ek < -900) ? 0.0 : ldexp(d, ej + ek - 2 * b);
+    G[(int64_t)kc * pl.m + jc] = g;
+    G[(int64_t)jc * pl.m + kc] = g;
+  }
 }
 
 }  // namespace scs

@@ -485,7 +485,7 @@ static int run_gram_i8(scs_problem* p, int* done) {
   }
   {
     StageTimer t(c, ST_GRAMFIN);
-    LAUNCH(c, k_crt, dim3((m + 63) / 64, (m + 3) / 4), 256, 0, p->d_i8partial, p->i8plan, p->d_ecol, p->i8_b, p->d_G);
+    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, p->i8plan, p->d_ecol, p->i8_b, p->d_G);
   }
   *done = 1;
   return SCS_OK;
@@ -536,16 +536,21 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   CU_TRY(cudaMemcpyAsync(tmp, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
   const int nblk = (m + kNB - 1) / kNB;
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+      attr_set = true;
+    }
+  }
+  double* rdiag = Linv;  // first m doubles of the workspace hold 1/L_jj
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * kNB;
     const int nb = std::min(kNB, m - k0);
-    LAUNCH(c, k_potf2, 1, 256, 0, M, (int64_t)m, m, k0, Linv + (size_t)k * kNB * kNB, d_info);
     const int rem = m - k0 - nb;
-    if (rem > 0) {
-      const int rb = (rem + kNB - 1) / kNB;
-      LAUNCH(c, k_trsm_panel, rb, 256, 0, M, (int64_t)m, m, k0, Linv + (size_t)k * kNB * kNB);
-      LAUNCH(c, k_syrk_update, rb * (rb + 1) / 2, 256, 0, M, (int64_t)m, m, k0);
-    }
+    const int rb = (rem + kNB - 1) / kNB;
+    LAUNCH(c, k_panel, 1 + rb, 256, 0, M, (int64_t)m, m, k0, rdiag, d_info);
+    if (rem > 0) LAUNCH(c, k_syrk_update, rb * (rb + 1) / 2, 128, kTileSmem, M, (int64_t)m, m, k0);
   }
   int info = 0;
   CU_TRY(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -555,14 +560,12 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
     for (int k = 0; k < nblk; ++k) {
       const int k0 = k * kNB, nb = std::min(kNB, m - k0);
       const int rem = m - k0 - nb;
-      LAUNCH(c, k_fwd_step, std::max(1, (rem + 255) / 256), 256, 0, M, (int64_t)m, m, k0,
-             Linv + (size_t)k * kNB * kNB, b, tmp);
+      LAUNCH(c, k_fwd_step, std::max(1, (rem + 255) / 256), 256, 0, M, (int64_t)m, m, k0, rdiag, b, tmp);
     }
     // tmp now holds y
     for (int k = nblk - 1; k >= 0; --k) {
       const int k0 = k * kNB;
-      LAUNCH(c, k_bwd_step, std::max(1, (k0 + 255) / 256), 256, 0, M, (int64_t)m, m, k0,
-             Linv + (size_t)k * kNB * kNB, tmp, dsol);
+      LAUNCH(c, k_bwd_step, std::max(1, (k0 + 255) / 256), 256, 0, M, (int64_t)m, m, k0, rdiag, tmp, dsol);
     }
     *used_fallback = 0;
     return SCS_OK;
