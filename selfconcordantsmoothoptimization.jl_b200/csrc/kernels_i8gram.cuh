@@ -39,6 +39,8 @@ constexpr int kI8ChunkRows = 65536;       // 128*128*65536 = 2^30 < 2^31
 constexpr uint32_t kI8TmemCols = 512;     // two 256-column int32 accumulators
 constexpr int kI8Cluster = 4;             // CTAs per cluster: 4 vertically adjacent tiles, B slab multicast (64 rows each)
 constexpr int kI8BPart = kI8BN / kI8Cluster;  // rows of the B slab each CTA fetches and multicasts
+constexpr int kI8SegKb = 64;              // producers re-align every 64 k-blocks (8192 rows): keeps all clusters inside
+                                          // one L2-sized window of the plane so operand panels are shared, not re-read
 
 struct I8Plan {
   int m;
@@ -257,7 +259,8 @@ SCS_DEVINL void i8_unit(const I8Plan& pl, int64_t u, int& l, int& c, int& t) {
 // it fetches its own A slab and rows [r*kI8BPart, (r+1)*kI8BPart) of the shared B slab, multicast to the whole cluster.
 __global__ void __launch_bounds__(kI8Threads, 1)
 k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap bmap, I8Plan pl,
-         const int2* __restrict__ tiles, int8_t* __restrict__ partial /* [nmod][nchunks][m][ldp] */) {
+         const int2* __restrict__ tiles, int8_t* __restrict__ partial /* [nmod][nchunks][m][ldp] */,
+         unsigned long long* __restrict__ progress /* zeroed before the launch */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = (uint64_t*)(smem + kI8Stages * kI8StageBytes);
@@ -296,25 +299,57 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // All CTAs are co-resident (the grid is sized by cudaOccupancyMaxActiveClusters), so the producers can keep in
+    // step through a global counter: before issuing segment t every producer has finished issuing segment t-1.
+    // The wait has a bounded spin: if the assumption were ever violated the kernel degrades to free-running.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = cid; u < pl.units; u += ncl) {
-        int l, c, t;
-        i8_unit(pl, u, l, c, t);
-        const int2 tile = tiles[t];
+      const int64_t steps = (pl.units + ncl - 1) / ncl;
+      const int segs = (int)((pl.chunk_kblocks + kI8SegKb - 1) / kI8SegKb);
+      const unsigned long long ncta = gridDim.x;
+      bool in_step = true;
+      for (int64_t st = 0; st < steps; ++st) {
+        const int64_t u = cid + st * ncl;
+        const bool valid = u < pl.units;
+        int l = 0, c = 0, t = 0;
+        if (valid) i8_unit(pl, u, l, c, t);
+        const int2 tile = valid ? tiles[t] : make_int2(0, 0);
         const int64_t kb0 = (int64_t)c * pl.chunk_kblocks;
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
-        for (int64_t kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);  // all CTAs of the cluster have consumed this slot
-          mbar_expect_tx(&full[stage], kI8StageBytes);
-          uint8_t* sa = smem + stage * kI8StageBytes;
-          tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
-          tma_load_3d_mc(sa + kI8ABytes + crank * (kI8BPart * kI8BK), &bmap, &full[stage], (int)(kb * kI8BK),
-                         tile.y * kI8BN + crank * kI8BPart, l, kMask);
-          if (++stage == kI8Stages) {
-            stage = 0;
-            phase ^= 1;
+        for (int sg = 0; sg < segs; ++sg) {
+          const unsigned long long point = (unsigned long long)(st * segs + sg);
+          if (point > 0) {
+            atomicAdd(progress, 1ULL);
+            if (in_step) {
+              const unsigned long long want = point * ncta;
+              int spins = 0;
+              while (true) {
+                unsigned long long seen;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(progress) : "memory");
+                if (seen >= want) break;
+                if (++spins > 40000) {  // ~4 ms: give up on lock-step, keep computing
+                  in_step = false;
+                  break;
+                }
+                __nanosleep(100);
+              }
+            }
+          }
+          if (!valid) continue;
+          const int64_t s0 = kb0 + (int64_t)sg * kI8SegKb;
+          const int64_t s1 = s0 + kI8SegKb < kb1 ? s0 + kI8SegKb : kb1;
+          for (int64_t kb = s0; kb < s1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);  // all CTAs of the cluster have consumed this slot
+            mbar_expect_tx(&full[stage], kI8StageBytes);
+            uint8_t* sa = smem + stage * kI8StageBytes;
+            tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
+            tma_load_3d_mc(sa + kI8ABytes + crank * (kI8BPart * kI8BK), &bmap, &full[stage], (int)(kb * kI8BK),
+                           tile.y * kI8BN + crank * kI8BPart, l, kMask);
+            if (++stage == kI8Stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }

@@ -188,6 +188,7 @@ struct scs_problem {
   double *d_colmax = nullptr, *d_wstat = nullptr, *d_colscale = nullptr;
   int* d_ecol = nullptr;
   int2* d_i8tiles = nullptr;
+  unsigned long long* d_i8progress = nullptr;
   int64_t ldx = 0;
   int i8_b = 0, i8_clusters = 0;
   I8Plan i8plan{};
@@ -408,6 +409,7 @@ static int i8_setup(scs_problem* p) {
   SCS_TRY(dalloc(&p->d_colscale, m));
   CU_TRY(cudaMalloc((void**)&p->d_ecol, m * sizeof(int)));
   CU_TRY(cudaMalloc((void**)&p->d_i8tiles, tiles.size() * sizeof(int2)));
+  CU_TRY(cudaMalloc((void**)&p->d_i8progress, sizeof(unsigned long long)));
   CU_TRY(cudaMemcpyAsync(p->d_i8tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   // P/2 > n * 2^(2b)
@@ -478,8 +480,9 @@ static int run_gram_i8(scs_problem* p, int* done) {
     }
     const int ncl = (int)std::min<int64_t>(p->i8_clusters, p->i8plan.units);
     cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
+    CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
     cudaError_t le = cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, p->i8plan, (const int2*)p->d_i8tiles,
-                                        p->d_i8partial);
+                                        p->d_i8partial, p->d_i8progress);
     c->launches += 1;
     if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
   }
@@ -750,7 +753,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_ecol, p->d_i8tiles};
+                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
