@@ -37,9 +37,15 @@ constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 + 256;
 constexpr int kI8Threads = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int kI8ChunkRows = 65536;       // 128*128*65536 = 2^30 < 2^31
 constexpr uint32_t kI8TmemCols = 512;     // two 256-column int32 accumulators
-constexpr int kI8Cluster = 4;             // CTAs per cluster: 4 vertically adjacent tiles, B slab multicast (64 rows each)
+#ifndef SCS_I8_CLUSTER
+#define SCS_I8_CLUSTER 4
+#endif
+#ifndef SCS_I8_SEGKB
+#define SCS_I8_SEGKB 64
+#endif
+constexpr int kI8Cluster = SCS_I8_CLUSTER;             // CTAs per cluster: 4 vertically adjacent tiles, B slab multicast (64 rows each)
 constexpr int kI8BPart = kI8BN / kI8Cluster;  // rows of the B slab each CTA fetches and multicasts
-constexpr int kI8SegKb = 64;              // producers re-align every 64 k-blocks (8192 rows): keeps all clusters inside
+constexpr int kI8SegKb = SCS_I8_SEGKB;              // producers re-align every 64 k-blocks (8192 rows): keeps all clusters inside
                                           // one L2-sized window of the plane so operand panels are shared, not re-read
 
 struct I8Plan {

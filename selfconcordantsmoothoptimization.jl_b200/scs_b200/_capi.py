@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libscs_b200.so")
+LIB_PATH = os.environ.get("SCS_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libscs_b200.so")
 
 SCS_OK, SCS_INVALID_ARG, SCS_UNSUPPORTED, SCS_NOT_SPD, SCS_CUDA_ERROR, SCS_NCCL_ERROR, SCS_OOM, SCS_STATE_ERROR = range(8)
 

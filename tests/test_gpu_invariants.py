@@ -58,3 +58,26 @@ def test_run_to_run_bitwise_reproducible(scs):
         p.close()
     assert np.array_equal(sols[0].x, sols[1].x)
     assert sols[0].obj == sols[1].obj
+
+
+def test_i8_gram_agrees_with_dmma_at_scale(scs):
+    """At a size the numpy oracle cannot reach, the emulated-fp64 (tcgen05 int8 + CRT) Gram and the native DMMA Gram
+    must give the same solver iterates to the 1e-10 bar (several K chunks, lock-stepped clusters, b = 48-bit fixed
+    point), and the Gram entries must agree to ~1e-13 of the diagonal scale."""
+    n, m = 400_000, 1024
+    x0 = synth.make_x0(m)
+    sols, grams = {}, {}
+    for mode in ("dmma", "i8"):
+        p = scs.Problem.synthetic(n, m, scs.LogisticLoss(1 / n, "consistent"), 1e-3, x0=x0)
+        p.set_gram_mode(mode)
+        grams[mode] = p.gram(x0 * 0.3, weights="ggn")
+        assert p.gram_path() == mode
+        sols[mode] = scs.iterate(scs.ProxGGNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=6, alpha=1,
+                                 verbose=0, device_loop=True)
+        p.close()
+    d = np.sqrt(np.diag(grams["dmma"]))
+    assert np.max(np.abs(grams["i8"] - grams["dmma"]) / np.outer(d, d)) <= 1e-12
+    a, b = sols["i8"], sols["dmma"]
+    assert np.linalg.norm(a.x - b.x) <= 1e-10 * np.linalg.norm(b.x)
+    assert max(abs(u - v) / abs(v) for u, v in zip(a.obj, b.obj)) <= 1e-10
+    assert np.array_equal(a.x != 0, b.x != 0)
