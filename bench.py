@@ -234,10 +234,28 @@ def run_reference(args, wl, rank, world):
             "cpu_baseline": {"value": val, "unit": "iters/sec", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, …) was
+    re-routed to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -431,7 +449,7 @@ def main():
                 "stages_ms_per_step": {k: v[0] / K for k, v in stages.items() if v[1]},
                 "cpu_baseline": cpu, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sus},
                 "gram_path": gram_path, "gram_fp64_equivalent": gram_equiv}
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.close()
     if world > 1:
         dist.barrier()
