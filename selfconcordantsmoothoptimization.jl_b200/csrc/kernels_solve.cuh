@@ -26,11 +26,18 @@ constexpr int kLS = kNB + 1;
 SCS_DEVINL double quad_bcast(double v, int src_slice) {
   return __shfl_sync(0xffffffffu, v, (threadIdx.x & 28) | src_slice);
 }
+// Grid: CTA 0 stores the factored diagonal block; CTAs 1..rb substitute 64 rows of the panel each; the last CTA
+// (index 1 + rb) carries the right-hand side as one more row: y_k = L_kk^-1 b_k (forward substitution is folded into
+// the factorisation; the matching update of b below the block is done by k_syrk_update's GEMV CTAs).
+// The register window a[0..15] always starts at the current column group (it is rotated after every four columns), so
+// the column loop is a compact runtime loop with static register indices.
 __global__ void __launch_bounds__(256) k_panel(double* __restrict__ M, int64_t ld, int m, int k0,
-                                               double* __restrict__ rdiag_g, int* __restrict__ info) {
+                                               double* __restrict__ rdiag_g, int* __restrict__ info,
+                                               double* __restrict__ bvec, double* __restrict__ yvec, int rb) {
   __shared__ double Ls[kNB * kLS];   // factored diagonal block, Ls[r][c]
   __shared__ double colraw[2][kNB];  // column j before scaling
   __shared__ double rds[kNB];        // 1 / L_jj
+  __shared__ double bk[kNB];
   const int nb = min(kNB, m - k0);
   const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
   double a[16];
@@ -39,39 +46,63 @@ __global__ void __launch_bounds__(256) k_panel(double* __restrict__ M, int64_t l
     const int c = 4 * k + q;
     a[k] = (r < nb && c < nb && c <= r) ? M[(int64_t)(k0 + c) * ld + k0 + r] : ((r == c) ? 1.0 : 0.0);
   }
+  // Entries above the diagonal (c > r) are carried along but never consumed: the per-element triangle test is not
+  // needed, only the uniform "window still inside the block" bound (k < 16 - kk).
+#pragma unroll 1
+  for (int kk = 0; kk < 16; ++kk) {
+    const int kleft = 16 - kk;
 #pragma unroll
-  for (int j = 0; j < kNB; ++j) {
-    const int kq = j & 3, kk = j >> 2;
-    if (q == kq) colraw[j & 1][r] = a[kk];
-    __syncthreads();
-    const double piv = colraw[j & 1][j];
-    if (blockIdx.x == 0 && tid == 0 && j < nb && !(piv > 0.0) && info[0] == 0) info[0] = k0 + j + 1;
-    const double rd = rsqrt(piv);
-    const double lij = (r > j) ? colraw[j & 1][r] * rd : 0.0;
-    if (q == kq) {
-      if (r > j) a[kk] = lij;
-      if (r == j) {
-        a[kk] = piv * rd;
-        rds[j] = rd;
+    for (int kq = 0; kq < 4; ++kq) {
+      const int j = 4 * kk + kq;
+      if (q == kq) colraw[kq & 1][r] = a[0];
+      __syncthreads();
+      const double* cr = colraw[kq & 1];
+      const double piv = cr[j];
+      if (blockIdx.x == 0 && tid == 0 && j < nb && !(piv > 0.0) && info[0] == 0) info[0] = k0 + j + 1;
+      const double rd = rsqrt(piv);
+      const double lij = (r > j) ? cr[r] * rd : 0.0;
+      if (q == kq) {
+        if (r > j) a[0] = lij;
+        if (r == j) {
+          a[0] = piv * rd;
+          rds[j] = rd;
+        }
       }
-    }
+      const double lr = lij * rd;  // L[r][j] / L[j][j]: the update uses the unscaled column
+      const double* crq = cr + 4 * kk + q;
+      if (q > kq) a[0] = fma(-lr, crq[0], a[0]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int c = 4 * k + q;
-      if (4 * k + 3 > j) {  // compile-time prune: no column of this register group is right of j otherwise
-        if (c > j && c <= r) a[k] -= lij * (colraw[j & 1][c] * rd);
-      }
+      for (int k = 1; k < 16; ++k)
+        if (k < kleft) a[k] = fma(-lr, crq[4 * k], a[k]);
     }
-  }
+    // column group kk is final: park it in shared memory and rotate the window
+    Ls[r * kLS + 4 * kk + q] = (4 * kk + q <= r) ? a[0] : 0.0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int c = 4 * k + q;
-    Ls[r * kLS + c] = (c <= r) ? a[k] : 0.0;
-    if (blockIdx.x == 0 && r < nb && c < nb && c <= r) M[(int64_t)(k0 + c) * ld + k0 + r] = a[k];
+    for (int k = 0; k < 15; ++k) a[k] = a[k + 1];
+    a[15] = 0.0;
   }
   __syncthreads();
   if (blockIdx.x == 0) {
+    for (int e = tid; e < kNB * kNB; e += 256) {
+      const int rr = e & 63, c = e >> 6;
+      if (rr < nb && c < nb && c <= rr) M[(int64_t)(k0 + c) * ld + k0 + rr] = Ls[rr * kLS + c];
+    }
     if (tid < nb) rdiag_g[k0 + tid] = rds[tid];
+    return;
+  }
+  if ((int)blockIdx.x == 1 + rb) {  // right-hand-side row
+    if (tid < kNB) bk[tid] = tid < nb ? bvec[k0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 32) {
+      for (int c = 0; c < nb; ++c) {
+        const double yc = bk[c] * rds[c];
+        if (tid == 0) yvec[k0 + c] = yc;
+        const int r0 = tid, r1 = tid + 32;
+        if (r0 > c) bk[r0] -= Ls[r0 * kLS + c] * yc;
+        if (r1 > c) bk[r1] -= Ls[r1 * kLS + c] * yc;
+        __syncwarp();
+      }
+    }
     return;
   }
   // ---- rows below: X L11' = A21  ->  x_:c = (a_:c - sum_{p<c} x_:p L[c][p]) / L[c][c], right-looking over c
@@ -82,23 +113,25 @@ __global__ void __launch_bounds__(256) k_panel(double* __restrict__ M, int64_t l
     const int c = 4 * k + q;
     x[k] = (row < m && c < nb) ? M[(int64_t)(k0 + c) * ld + row] : 0.0;
   }
+#pragma unroll 1
+  for (int kc = 0; kc < 16; ++kc) {
+    const int kleft = 16 - kc;
 #pragma unroll
-  for (int c = 0; c < kNB; ++c) {
-    const int kq = c & 3, kk = c >> 2;
-    const double xc = quad_bcast(x[kk] * rds[c], kq);  // only slice kq's value is used
-    if (q == kq) x[kk] = xc;
+    for (int cq = 0; cq < 4; ++cq) {
+      const int c = 4 * kc + cq;
+      const double xc = quad_bcast(x[0] * rds[c], cq);  // slice cq owns column c
+      if (q == cq) x[0] = xc;
+      const double* lc = Ls + (4 * kc + q) * kLS + c;  // L[cp][c] for cp = 4*(kc+k)+q
+      if (q > cq) x[0] = fma(-xc, lc[0], x[0]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int cp = 4 * k + q;
-      if (4 * k + 3 > c) {
-        if (cp > c) x[k] -= xc * Ls[cp * kLS + c];
-      }
+      for (int k = 1; k < 16; ++k)
+        if (k < kleft) x[k] = fma(-xc, lc[4 * k * kLS], x[k]);
     }
-  }
+    const int cst = 4 * kc + q;
+    if (row < m && cst < nb) M[(int64_t)(k0 + cst) * ld + row] = x[0];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int c = 4 * k + q;
-    if (row < m && c < nb) M[(int64_t)(k0 + c) * ld + row] = x[k];
+    for (int k = 0; k < 15; ++k) x[k] = x[k + 1];
+    x[15] = 0.0;
   }
 }
 
@@ -158,13 +191,36 @@ SCS_DEVINL void load_tile_T(double* dst, const double* __restrict__ M, int64_t l
   }
 }
 
-// Trailing update A22 -= L21 * L21'  (lower 64x64 tiles only).  grid = (#tiles in the lower triangle), 128 threads.
-__global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0) {
+// Trailing update A22 -= L21 * L21'  (lower 64x64 tiles only) on CTAs [0, ntiles); CTAs >= ntiles update the
+// right-hand side below the block: b_i -= sum_c L[i, k0+c] y_c (128 rows each).  128 threads.
+__global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0, int ntiles,
+                                                     double* __restrict__ bvec, const double* __restrict__ yvec) {
   extern __shared__ double tile_sh[];
   double* As = tile_sh;
   double* Bs = tile_sh + kNB * kTS;
   const int nb = min(kNB, m - k0);
   const int base = k0 + nb;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= ntiles) {
+    if (tid < kNB) As[tid] = tid < nb ? yvec[k0 + tid] : 0.0;
+    __syncthreads();
+    const int row = base + ((int)blockIdx.x - ntiles) * 128 + tid;
+    if (row < m) {
+      const double* rp = M + (int64_t)k0 * ld + row;
+      double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+      int c = 0;
+      for (; c + 16 <= nb; c += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = rp[(int64_t)(c + u) * ld];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) sacc[u & 3] = fma(v[u], As[c + u], sacc[u & 3]);
+      }
+      for (; c < nb; ++c) sacc[0] = fma(rp[(int64_t)c * ld], As[c], sacc[0]);
+      bvec[row] -= (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
+    }
+    return;
+  }
   int ti, tj;
   {
     const int tt = blockIdx.x;
@@ -175,7 +231,6 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
     tj = tt - r * (r + 1) / 2;
   }
   const int r0 = base + ti * kNB, c0 = base + tj * kNB;
-  const int tid = threadIdx.x;
   load_tile_T(As, M, ld, m, k0, r0, nb, tid);
   if (ti == tj) {
     Bs = As;  // diagonal tile: both operands are the same panel rows
@@ -185,6 +240,17 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  // issue the read half of the read-modify-write before the MMAs so its latency hides behind them
+  double old[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
+        old[i][j][h] = (row < m && col < m && row >= col) ? M[(int64_t)col * ld + row] : 0.0;
+      }
   double acc[4][4][2] = {};
   tile_mma_64(As, Bs, wm, wn, g, t, acc);
 #pragma unroll
@@ -194,7 +260,7 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
-        if (row < m && col < m && row >= col) M[(int64_t)col * ld + row] -= acc[i][j][h];
+        if (row < m && col < m && row >= col) M[(int64_t)col * ld + row] = old[i][j][h] - acc[i][j][h];
       }
 }
 
@@ -209,51 +275,6 @@ SCS_DEVINL void load_diag_block(double* Ls, const double* __restrict__ M, int64_
   }
 #pragma unroll
   for (int u = 0; u < 16; ++u) Ls[r * kLS + cb + 4 * u] = v[u];
-}
-
-// Forward substitution step for block k (L y = b): every CTA solves L_kk y_k = b_k itself (one warp, 64 sequential
-// columns), CTA 0 stores y_k, and CTA c updates its 256 rows below: b_i -= sum_c L[i, k0+c] y_c.
-__global__ void __launch_bounds__(256) k_fwd_step(const double* __restrict__ M, int64_t ld, int m, int k0,
-                                                  const double* __restrict__ rdiag_g, double* __restrict__ b,
-                                                  double* __restrict__ y) {
-  __shared__ double Ls[kNB * kLS];
-  __shared__ double bk[kNB], yk[kNB], rd[kNB];
-  const int nb = min(kNB, m - k0);
-  const int tid = threadIdx.x;
-  load_diag_block(Ls, M, ld, k0, nb, tid);
-  if (tid < kNB) {
-    bk[tid] = tid < nb ? b[k0 + tid] : 0.0;
-    rd[tid] = tid < nb ? rdiag_g[k0 + tid] : 0.0;
-  }
-  // prefetch this thread's row of the panel while warp 0 runs the substitution
-  const int row = k0 + nb + blockIdx.x * 256 + tid;
-  __syncthreads();
-  if (tid < 32) {
-    for (int c = 0; c < nb; ++c) {
-      const double yc = bk[c] * rd[c];
-      if (tid == 0) yk[c] = yc;
-      const int r0 = tid, r1 = tid + 32;
-      if (r0 > c) bk[r0] -= Ls[r0 * kLS + c] * yc;
-      if (r1 > c) bk[r1] -= Ls[r1 * kLS + c] * yc;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (row < m) {
-    const double* rp = M + (int64_t)k0 * ld + row;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    int c = 0;
-    for (; c + 16 <= nb; c += 16) {
-      double v[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = rp[(int64_t)(c + u) * ld];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) s[u & 3] = fma(v[u], yk[c + u], s[u & 3]);
-    }
-    for (; c < nb; ++c) s[0] = fma(rp[(int64_t)c * ld], yk[c], s[0]);
-    b[row] -= (s[0] + s[1]) + (s[2] + s[3]);
-  }
-  if (blockIdx.x == 0 && tid < nb) y[k0 + tid] = yk[tid];
 }
 
 // Backward substitution step for block k (L' d = y), right-looking: solve L_kk' d_k = y_k, then for every column

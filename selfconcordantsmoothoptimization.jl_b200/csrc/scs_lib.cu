@@ -536,35 +536,39 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
                      double* dsol, int m, int* used_fallback) {
   StageTimer t(c, ST_SOLVE);
   CU_TRY(cudaMemcpyAsync(Msave, M, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  CU_TRY(cudaMemcpyAsync(tmp, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  // the LU fallback needs the untouched right-hand side: keep it in dsol until the factorisation has succeeded
+  CU_TRY(cudaMemcpyAsync(dsol, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
   const int nblk = (m + kNB - 1) / kNB;
   {
     static bool attr_set = false;
     if (!attr_set) {
       CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+      // same shared-memory carve-out for every kernel of the sequence: no SM reconfiguration between launches
+      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_bwd_step, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr_set = true;
     }
   }
   double* rdiag = Linv;  // first m doubles of the workspace hold 1/L_jj
+  // b rides along as an extra row of the factorisation: tmp receives y = L^-1 b block by block
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * kNB;
     const int nb = std::min(kNB, m - k0);
     const int rem = m - k0 - nb;
     const int rb = (rem + kNB - 1) / kNB;
-    LAUNCH(c, k_panel, 1 + rb, 256, 0, M, (int64_t)m, m, k0, rdiag, d_info);
-    if (rem > 0) LAUNCH(c, k_syrk_update, rb * (rb + 1) / 2, 128, kTileSmem, M, (int64_t)m, m, k0);
+    LAUNCH(c, k_panel, 2 + rb, 256, 0, M, (int64_t)m, m, k0, rdiag, d_info, b, tmp, rb);
+    if (rem > 0) {
+      const int ntiles = rb * (rb + 1) / 2;
+      LAUNCH(c, k_syrk_update, ntiles + (rem + 127) / 128, 128, kTileSmem, M, (int64_t)m, m, k0, ntiles, b,
+             (const double*)tmp);
+    }
   }
   int info = 0;
   CU_TRY(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   if (info == 0) {
-    // L y = b (y -> dsol as scratch), then L' d = y (d -> dsol)
-    for (int k = 0; k < nblk; ++k) {
-      const int k0 = k * kNB, nb = std::min(kNB, m - k0);
-      const int rem = m - k0 - nb;
-      LAUNCH(c, k_fwd_step, std::max(1, (rem + 255) / 256), 256, 0, M, (int64_t)m, m, k0, rdiag, b, tmp);
-    }
     // tmp now holds y
     for (int k = nblk - 1; k >= 0; --k) {
       const int k0 = k * kNB;
@@ -575,6 +579,7 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   }
   // not positive definite: partial-pivoting LU on the saved copy (symmetrised), still on the device
   *used_fallback = 1;
+  CU_TRY(cudaMemcpyAsync(b, dsol, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, Msave, (int64_t)m, m);
   // restore b (the Cholesky path has not touched b yet, but keep the contract explicit)
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
