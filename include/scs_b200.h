@@ -113,6 +113,12 @@ int scs_set_L(scs_problem* p, int has_L, double L);
  * scs_get_gram_path reports what the last Gram used (1 = DMMA, 2 = tcgen05 int8). */
 int scs_set_gram_mode(scs_problem* p, int mode);
 int scs_get_gram_path(scs_problem* p, int* path);
+/* Streaming-pass selection for "objective + gradient at the same x": 0 = auto (the single-pass cluster kernel
+ * k_fused_grad when m <= 4096, else two passes), 1 = always two passes (k_forward + k_adjoint), 2 = fused, and
+ * SCS_UNSUPPORTED if the shape has no fused kernel.  scs_get_stream_path reports what the last gradient used
+ * (1 = two passes, 2 = fused). */
+int scs_set_stream_mode(scs_problem* p, int mode);
+int scs_get_stream_path(scs_problem* p, int* path);
 int scs_method_init(scs_problem* p);
 
 /* ---- the two call sites of optim_loop! ------------------------------------------------- */
@@ -144,12 +150,14 @@ int scs_prox(scs_problem* p, const double* u, const double* hr, double ss, doubl
 int scs_reg_value(scs_problem* p, const double* x, double* out);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
-/* Kernel launches issued by this context since creation / last reset, and device milliseconds of the last
- * scs_step / scs_objective broken down by stage.  stage ids: 0 forward, 1 adjoint, 2 gram, 3 solve, 4 vector,
- * 5 allreduce, 6 fused forward+adjoint, 7 gram finalize (split sum + mirror). */
+/* Kernel launches issued by this context since creation / last reset, and device milliseconds accumulated per
+ * stage while profiling is on.  stage ids: 0 forward, 1 adjoint, 2 gram, 3 solve, 4 vector, 5 allreduce,
+ * 6 fused forward+adjoint (single pass), 7 gram finalize (split sum + mirror / CRT), 8 residue planes of the
+ * emulated-fp64 Gram, 9 reserved.  ms / calls: arrays of SCS_NUM_STAGES entries. */
+#define SCS_NUM_STAGES 10
 int scs_get_counters(scs_ctx* ctx, int64_t* launches, int reset);
 int scs_set_profiling(scs_ctx* ctx, int enable);
-int scs_get_stage_ms(scs_ctx* ctx, double* ms8, int64_t* calls8, int reset);
+int scs_get_stage_ms(scs_ctx* ctx, double* ms, int64_t* calls, int reset);
 
 #ifdef __cplusplus
 }

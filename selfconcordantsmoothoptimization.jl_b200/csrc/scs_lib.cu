@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels_gram.cuh"
 #include "kernels_i8gram.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_vec.cuh"
@@ -51,7 +52,10 @@ static NcclApi g_nccl;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-enum { ST_FWD = 0, ST_ADJ = 1, ST_GRAM = 2, ST_SOLVE = 3, ST_VEC = 4, ST_COMM = 5, ST_FUSED = 6, ST_GRAMFIN = 7, ST_N = 8 };
+enum {
+  ST_FWD = 0, ST_ADJ = 1, ST_GRAM = 2, ST_SOLVE = 3, ST_VEC = 4, ST_COMM = 5, ST_FUSED = 6, ST_GRAMFIN = 7, ST_RESID = 8,
+  ST_N = SCS_NUM_STAGES
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -193,6 +197,13 @@ struct scs_problem {
   int i8_b = 0, i8_clusters = 0;
   I8Plan i8plan{};
   CUtensorMap xmap{}, xmap_b{};
+  // single-pass fused gradient (kernels_fused.cuh)
+  int stream_mode = 0;       // 0 auto, 1 two passes (k_forward + k_adjoint), 2 fused whenever the shape is supported
+  int last_stream_path = 0;  // 1 two passes, 2 fused
+  bool fu_ready = false, fu_failed = false;
+  int fu_cluster = 1, fu_clusters = 0;
+  CUtensorMap fumap{};
+  double *d_fupart = nullptr, *d_fuloss = nullptr;
   // l-bfgs
   double *d_S = nullptr, *d_Y = nullptr;
   int64_t* d_state = nullptr;
@@ -251,6 +262,125 @@ static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
   return SCS_OK;
 }
 
+// ---- single-pass fused gradient ---------------------------------------------------------------------------------
+static void fused_config(scs_problem* p, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3((unsigned)(nclusters * p->fu_cluster));
+  cfg->blockDim = dim3(kFuThreads);
+  cfg->dynamicSmemBytes = kFuSmemBytes;
+  cfg->stream = p->ctx->stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p->fu_cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+
+// The shape decides the cluster geometry: CTA rank c owns columns [256c, 256c + 256); at most 16 CTAs per cluster.
+static bool fused_shape(const scs_problem* p, int* cluster) {
+  if (p->loss.kind == SCS_LOSS_QUADFORM) return false;
+  if (p->ldd >= (int64_t)1 << 31) return false;  // TMA coordinates are 32-bit
+  const int64_t cl = (p->m + kFuCols - 1) / kFuCols;
+  if (cl > kFuMaxCluster) return false;
+  *cluster = (int)cl;
+  return true;
+}
+
+static int fused_setup(scs_problem* p) {
+  if (p->fu_ready) return SCS_OK;
+  scs_ctx* c = p->ctx;
+  if (!fused_shape(p, &p->fu_cluster)) {
+    p->fu_failed = true;
+    return fail(SCS_UNSUPPORTED, "fused gradient pass: shape not supported (m > 4096 or quadform loss)");
+  }
+  if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)p->ldd, (cuuint64_t)p->m};
+  cuuint64_t gstride[1] = {(cuuint64_t)p->ldd * 8};
+  cuuint32_t box[2] = {(cuuint32_t)kFuStageRows, (cuuint32_t)kFuBoxCols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(&p->fumap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->dA, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (fused pass) failed: " + std::to_string((int)r));
+  CU_TRY(cudaFuncSetAttribute(k_fused_grad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(k_fused_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
+  if (p->fu_cluster > 8) {
+    CU_TRY(cudaFuncSetAttribute(k_fused_grad<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU_TRY(cudaFuncSetAttribute(k_fused_grad<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fused_config(p, &cfg, attr, c->num_sms / p->fu_cluster);
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, k_fused_grad<false>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    ncl = 0;
+  }
+  if (ncl < 1) {
+    p->fu_failed = true;
+    return fail(SCS_UNSUPPORTED, "fused gradient pass: no cluster of " + std::to_string(p->fu_cluster) + " CTAs can be resident");
+  }
+  p->fu_clusters = ncl;
+  SCS_TRY(dalloc(&p->d_fupart, (size_t)ncl * p->m));
+  SCS_TRY(dalloc(&p->d_fuloss, (size_t)ncl * p->fu_cluster));
+  p->fu_ready = true;
+  return SCS_OK;
+}
+
+static bool fused_wanted(scs_problem* p) {
+  if (p->stream_mode == 1 || p->fu_failed) return false;
+  int cl;
+  if (p->stream_mode == 0 && !p->fu_ready && !fused_shape(p, &cl)) return false;
+  return true;
+}
+
+// one read of A: z, r, w, the local loss sum in d_gl[m] and the local A'r in d_gl[0..m)
+static int run_fused(scs_problem* p, const double* dx, int wk) {
+  scs_ctx* c = p->ctx;
+  SCS_TRY(fused_setup(p));
+  StageTimer t(c, ST_FUSED);
+  LossParams lp = p->loss;
+  lp.weight_kind = wk;
+  const int64_t npanels = p->ldd / kFuRows;
+  const int ncl = (int)std::min<int64_t>(p->fu_clusters, (npanels + 1) / 2);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fused_config(p, &cfg, attr, ncl);
+  cudaError_t le;
+  if (getenv("SCS_FUSED_PROF")) {  // tuning aid: per-CTA wait-cycle counters printed to stderr (synchronises)
+    long long* dprof = nullptr;
+    const size_t np = (size_t)cfg.gridDim.x * 8;
+    CU_TRY(cudaMalloc((void**)&dprof, np * sizeof(long long)));
+    CU_TRY(cudaMemsetAsync(dprof, 0, np * sizeof(long long), c->stream));
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<true>, p->fumap, dx, (const double*)p->dy, lp, p->n, npanels, (int)p->m,
+                            p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, dprof, atoi(getenv("SCS_FUSED_PROF")) == 2 ? 1 : 0);
+    std::vector<long long> h(np);
+    cudaMemcpyAsync(h.data(), dprof, np * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(dprof);
+    double s[8] = {0};
+    for (size_t i = 0; i < np; ++i) s[i % 8] += (double)h[i];
+    const double nb = (double)cfg.gridDim.x;
+    const double panels = (double)npanels / ncl;
+    fprintf(stderr,
+            "[k_fused_grad prof] clusters %d x %d, panels/cluster %.0f; mean cycles per CTA: total %.0f (%.0f per panel) | "
+            "warp0: wait full %.0f, wait rbar %.0f, busy A %.0f | producer wait empty %.0f | push wait pbar %.0f | loss: "
+            "wait zbar %.0f, busy %.0f\n",
+            ncl, p->fu_cluster, panels, s[0] / nb, s[0] / nb / panels, s[1] / nb, s[2] / nb, s[7] / nb, s[3] / nb,
+            s[4] / nb, s[5] / nb, s[6] / nb);
+  } else {
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<false>, p->fumap, dx, (const double*)p->dy, lp, p->n, npanels, (int)p->m,
+                            p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, (long long*)nullptr, 0);
+  }
+  c->launches += 1;
+  if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_fused_grad launch: ") + cudaGetErrorString(le));
+  LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_fupart, (int64_t)ncl, (int)p->m, p->d_gl);
+  LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_fuloss, (int64_t)ncl * p->fu_cluster, p->d_gl + p->m);
+  p->last_stream_path = 2;
+  return SCS_OK;
+}
+
 // forward pass at x (cached by id and weight kind); leaves z, r, w on the device and the local loss sum in d_gl[m]
 static int ensure_forward(scs_problem* p, XRef x, int wk) {
   if (p->fwd_id == x.id && p->fwd_wk == wk) return SCS_OK;
@@ -277,8 +407,21 @@ static int ensure_loss(scs_problem* p, XRef x, int wk) {
 }
 // gradient of f at x into d_gl[0..m) (all-reduced together with the loss sum)
 static int ensure_grad(scs_problem* p, XRef x, int wk) {
+  if (!(p->fwd_id == x.id && p->fwd_wk == wk) && fused_wanted(p)) {
+    int rc = run_fused(p, x.d, wk);
+    if (rc == SCS_OK) {
+      p->fwd_id = x.id;
+      p->fwd_wk = wk;
+      SCS_TRY(allreduce(p->ctx, p->d_gl, p->m + 1));
+      p->loss_reduced = true;
+      p->grad_id = x.id;
+      return SCS_OK;
+    }
+    if (!(rc == SCS_UNSUPPORTED && p->stream_mode == 0)) return rc;  // auto mode: fall through to the two-pass kernels
+  }
   SCS_TRY(ensure_forward(p, x, wk));
   if (p->grad_id == x.id) return SCS_OK;
+  p->last_stream_path = 1;
   scs_ctx* c = p->ctx;
   if (p->loss.kind == SCS_LOSS_QUADFORM) {
     // g = 0.5*(A x + A' x) + y ; the adjoint pass takes r := x (zero padded to ldd)
@@ -446,7 +589,7 @@ static int run_gram_i8(scs_problem* p, int* done) {
   const int m = (int)p->m;
   const bool const_w = p->loss.kind == SCS_LOSS_LEASTSQUARES;  // w = 1/denominator: planes never change
   if (!(const_w && p->i8_planes_valid)) {
-    StageTimer t(c, ST_FUSED);
+    StageTimer t(c, ST_RESID);
     LAUNCH(c, k_wstat, 1, kVecThreads, 0, p->dw, p->n, p->d_wstat);
     double st[2];
     CU_TRY(cudaMemcpyAsync(st, p->d_wstat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -758,7 +901,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress};
+                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
@@ -996,6 +1139,17 @@ extern "C" int scs_set_gram_mode(scs_problem* p, int mode) {
   p->gram_mode = mode;
   return SCS_OK;
 }
+extern "C" int scs_set_stream_mode(scs_problem* p, int mode) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (mode < 0 || mode > 2) return fail(SCS_INVALID_ARG, "stream mode must be 0 (auto), 1 (two passes) or 2 (fused)");
+  p->stream_mode = mode;
+  return SCS_OK;
+}
+extern "C" int scs_get_stream_path(scs_problem* p, int* path) {
+  if (!p || !path) return fail(SCS_INVALID_ARG, "NULL argument");
+  *path = p->last_stream_path;
+  return SCS_OK;
+}
 extern "C" int scs_get_gram_path(scs_problem* p, int* path) {
   if (!p || !path) return fail(SCS_INVALID_ARG, "NULL argument");
   *path = p->last_gram_path;
@@ -1070,6 +1224,8 @@ static int objective_device(scs_problem* p, XRef x) {
   // reuse whatever forward pass is cached for this x: the loss value does not depend on the weight kind
   if (p->fwd_id == x.id)
     SCS_TRY(ensure_loss(p, x, p->fwd_wk));
+  else if (p->has_method && p->has_sm && fused_wanted(p))
+    SCS_TRY(ensure_grad(p, x, wk));  // step! at the same x follows (iterate.jl:189 then :233): one read of A serves both
   else
     SCS_TRY(ensure_loss(p, x, wk));
   StageTimer t(p->ctx, ST_VEC);

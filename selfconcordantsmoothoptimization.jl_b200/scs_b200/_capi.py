@@ -21,14 +21,14 @@ REG_KINDS = {"l1": 0, "l2": 1, "indbox": 2, "gl": 3}
 SMOOTH_PHUBER_L1L2, SMOOTH_PHUBER_INDBOX, SMOOTH_PHUBER_GL, SMOOTH_EXP_INDBOX, SMOOTH_LOGEXP_INDBOX, SMOOTH_OSBA_L1L2, SMOOTH_OSBA_GL = range(7)
 METHOD_N, METHOD_GGN, METHOD_LQN = 0, 1, 2
 WEIGHTS_NEWTON, WEIGHTS_GGN = 0, 1
-STAGES = ("forward", "adjoint", "gram", "solve", "vector", "allreduce", "fused", "gram_finalize")
+STAGES = ("forward", "adjoint", "gram", "solve", "vector", "allreduce", "fused", "gram_finalize", "residues", "reserved")
 
 # every symbol include/scs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "scs_version", "scs_last_error", "scs_comm_unique_id", "scs_ctx_create", "scs_ctx_destroy", "scs_ctx_sync",
     "scs_ctx_stream", "scs_problem_create", "scs_problem_create_synthetic", "scs_problem_destroy",
     "scs_problem_read_rows", "scs_set_regularizer", "scs_set_smoother", "scs_set_method", "scs_set_L",
-    "scs_set_gram_mode", "scs_get_gram_path", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
+    "scs_set_gram_mode", "scs_get_gram_path", "scs_set_stream_mode", "scs_get_stream_path", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
     "scs_smoother_eval", "scs_prox", "scs_reg_value", "scs_get_counters", "scs_set_profiling", "scs_get_stage_ms",
 )
 
@@ -80,6 +80,8 @@ def lib():
         "scs_method_init": ([vp], i32),
         "scs_set_gram_mode": ([vp, i32], i32),
         "scs_get_gram_path": ([vp, C.POINTER(i32)], i32),
+        "scs_set_stream_mode": ([vp, i32], i32),
+        "scs_get_stream_path": ([vp, C.POINTER(i32)], i32),
         "scs_objective": ([vp, _dp, _dp, _dp], i32),
         "scs_step": ([vp, _dp, _dp, i64, _dp, _dp, _dp], i32),
         "scs_solve": ([vp, _dp, _dp, i64, dbl, dbl, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip], i32),

@@ -60,8 +60,8 @@ class Context:
         K.check(K.lib().scs_set_profiling(self._h, int(on)))
 
     def stage_ms(self, reset=False):
-        ms = np.zeros(8)
-        calls = np.zeros(8, dtype=np.int64)
+        ms = np.zeros(len(K.STAGES))
+        calls = np.zeros(len(K.STAGES), dtype=np.int64)
         K.check(K.lib().scs_get_stage_ms(self._h, K.dptr(ms), K.iptr(calls), int(reset)))
         return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(K.STAGES)}
 
@@ -310,6 +310,15 @@ class Problem:
         v = C.c_int()
         K.check(K.lib().scs_get_gram_path(self._h, C.byref(v)))
         return {0: None, 1: "dmma", 2: "i8"}[v.value]
+
+    def set_stream_mode(self, mode):
+        """"auto" | "two_pass" | "fused": how objective + gradient at the same x read A (once or twice)."""
+        K.check(K.lib().scs_set_stream_mode(self._h, {"auto": 0, "two_pass": 1, "fused": 2}[mode]))
+
+    def stream_path(self):
+        v = C.c_int()
+        K.check(K.lib().scs_get_stream_path(self._h, C.byref(v)))
+        return {0: None, 1: "two_pass", 2: "fused"}[v.value]
 
     def reg_value(self, x):
         v = C.c_double()

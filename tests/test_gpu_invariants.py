@@ -81,3 +81,27 @@ def test_i8_gram_agrees_with_dmma_at_scale(scs):
     assert np.linalg.norm(a.x - b.x) <= 1e-10 * np.linalg.norm(b.x)
     assert max(abs(u - v) / abs(v) for u, v in zip(a.obj, b.obj)) <= 1e-10
     assert np.array_equal(a.x != 0, b.x != 0)
+
+
+def test_fused_gradient_agrees_with_two_pass_at_scale(scs):
+    """Single-pass cluster kernel vs the k_forward + k_adjoint pair on a shard far beyond the oracle's reach:
+    same z, r, w (to rounding of the different dot-product order), same loss and gradient; bit-reproducible."""
+    n, m = 400_003, 2048
+    L = scs.LogisticLoss(1 / n, "consistent")
+    p = scs.Problem.synthetic(n, m, L, 1e-3)
+    x = synth.make_x0(m) * 0.3
+    out = {}
+    for mode in ("two_pass", "fused", "fused"):
+        p.set_stream_mode(mode)
+        p.loss_eval(0.1 * x, weights="ggn")  # evict the cached pass at x
+        out.setdefault(mode, []).append(p.loss_eval(x, weights="ggn", want_rows=True))
+        assert p.stream_path() == mode
+    (f0, g0, z0, r0, w0), = out["two_pass"]
+    (f1, g1, z1, r1, w1), (f2, g2, z2, r2, w2) = out["fused"]
+    assert f1 == f2 and np.array_equal(g1, g2) and np.array_equal(z1, z2)
+    assert abs(f1 - f0) <= 1e-13 * abs(f0)
+    assert np.max(np.abs(z1 - z0)) <= 1e-13 * np.max(np.abs(z0))
+    np.testing.assert_allclose(r1, r0, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(w1, w0, rtol=1e-11, atol=1e-300)
+    assert np.linalg.norm(g1 - g0) <= 1e-12 * np.linalg.norm(g0)
+    p.close()

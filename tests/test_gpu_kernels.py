@@ -27,7 +27,8 @@ SHAPES = [(1, 1), (5, 2), (100, 50), (511, 7), (513, 130), (1000, 33), (4096, 25
 
 @pytest.mark.parametrize("n,m", SHAPES)
 @pytest.mark.parametrize("loss", ["logistic", "logistic_consistent", "ls"])
-def test_forward_adjoint(scs, n, m, loss):
+@pytest.mark.parametrize("stream", ["two_pass", "fused"])
+def test_forward_adjoint(scs, n, m, loss, stream):
     A, y, x = logistic_problem(n, m)
     if loss == "ls":
         Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
@@ -36,15 +37,57 @@ def test_forward_adjoint(scs, n, m, loss):
         mode = "consistent" if loss.endswith("consistent") else "literal"
         Lo, Lg = O.LogisticLoss(1 / n, mode), scs.LogisticLoss(1 / n, mode)
     p = scs.Problem(A, y, x, Lg, 0.1)
+    p.set_stream_mode(stream)
     z = A @ x
     for wk in ("newton", "ggn"):
         fv, g, zg, rg, wg = p.loss_eval(x, weights=wk, want_rows=True)
+        assert p.stream_path() == stream
         r, w = (Lo.grad_weights(z, y), Lo.hess_weights(z, y)) if wk == "newton" else Lo.ggn_weights(z, y)
         assert relerr(zg, z) <= 1e-13
         assert abs(fv - Lo.f(A, y, x)) <= 1e-13 * abs(Lo.f(A, y, x))
         np.testing.assert_allclose(rg, r, rtol=1e-11, atol=1e-300)
         np.testing.assert_allclose(wg, w, rtol=1e-11, atol=1e-300)
         assert relerr(g, A.T @ r) <= 1e-12
+    p.close()
+
+
+# the single-pass cluster kernel across its geometries (1..16 CTAs of 256 columns per cluster); panel counts that
+# are odd, smaller than the cluster count, and several per cluster
+@pytest.mark.parametrize("n,m", [(16, 300), (47, 1024), (6000, 777), (5000, 2048), (700, 2300), (2100, 4096),
+                                 (300, 3000), (20000, 512), (33, 4000)])
+def test_fused_gradient_geometries(scs, n, m):
+    A, y, x = logistic_problem(n, m)
+    Lo, Lg = O.LogisticLoss(1 / n, "consistent"), scs.LogisticLoss(1 / n, "consistent")
+    p = scs.Problem(A, y, x, Lg, 0.1)
+    p.set_stream_mode("fused")
+    z = A @ x
+    fv, g, zg, rg, wg = p.loss_eval(x, weights="ggn", want_rows=True)
+    assert p.stream_path() == "fused"
+    r, w = Lo.ggn_weights(z, y)
+    assert relerr(zg, z) <= 1e-13
+    assert abs(fv - Lo.f(A, y, x)) <= 1e-13 * abs(Lo.f(A, y, x))
+    np.testing.assert_allclose(rg, r, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(wg, w, rtol=1e-11, atol=1e-300)
+    assert relerr(g, A.T @ r) <= 1e-12
+    # the two-pass kernels agree and a second fused call reproduces the first bit for bit
+    fv2, g2, *_ = p.loss_eval(0.5 * x, weights="ggn")
+    fv3, g3, *_ = p.loss_eval(x, weights="ggn")
+    assert fv3 == fv and np.array_equal(g3, g)
+    p.set_stream_mode("two_pass")
+    fv4, g4, *_ = p.loss_eval(0.5 * x, weights="ggn")
+    assert abs(fv4 - fv2) <= 1e-13 * abs(fv2) and relerr(g2, g4) <= 1e-12
+    p.close()
+
+
+def test_fused_unsupported_shape_is_rejected_or_falls_back(scs):
+    n, m = 64, 4100  # wider than 16 CTAs x 256 columns
+    A, y, x = logistic_problem(n, m)
+    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n), 0.1)
+    fv, g, *_ = p.loss_eval(x)  # auto: two passes
+    assert p.stream_path() == "two_pass"
+    p.set_stream_mode("fused")
+    with pytest.raises(scs.UnsupportedError):
+        p.loss_eval(2 * x)
     p.close()
 
 

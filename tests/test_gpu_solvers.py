@@ -75,6 +75,7 @@ def test_config_parity(scs, name, device_loop):
     so = O.iterate(mo, modelo, reg, ho, **kw)
     mg, modelg, reg, hg, kw = cases.build(name, scs)
     sg = scs.iterate(mg, modelg, reg, hg, verbose=0, device_loop=device_loop, **kw)
+    assert modelg.stream_path() == "fused"  # auto: one read of A per objective + gradient
     g = load_golden(name)
     tol = TOL if name != "c2b_logreg_ggn_literal" else 1e-7  # indefinite Gram, diverging iterates: ill-conditioned
     assert sg.epochs == so.epochs == g["epochs"]
@@ -91,6 +92,23 @@ def test_config_parity(scs, name, device_loop):
     np.testing.assert_allclose(pg[1:], po[1:], rtol=1e-7, atol=1e-14)
     if reg in ("l1", "gl"):
         assert [int(i) for i in np.nonzero(sg.x)[0]] == g["support"]
+    modelg.close()
+
+
+@pytest.mark.parametrize("name", cases.CASES)
+def test_config_parity_two_pass_stream(scs, name):
+    """The default (auto) runs the single-pass fused gradient kernel; the k_forward + k_adjoint pair must meet the
+    same bar."""
+    mo, modelo, reg, ho, kw = cases.build(name, O)
+    so = O.iterate(mo, modelo, reg, ho, **kw)
+    mg, modelg, reg, hg, kw = cases.build(name, scs)
+    modelg.set_stream_mode("two_pass")
+    sg = scs.iterate(mg, modelg, reg, hg, verbose=0, device_loop=True, **kw)
+    assert modelg.stream_path() == "two_pass"
+    tol = TOL if name != "c2b_logreg_ggn_literal" else 1e-7
+    assert sg.epochs == so.epochs
+    assert relerr(sg.x, so.x) <= tol
+    assert hist_err(sg.obj, so.obj) <= tol
     modelg.close()
 
 
