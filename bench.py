@@ -15,7 +15,8 @@ consistent labels.  A "step" is one solver iteration = objective f(x)+g(x) (iter
           A itself is uploaded once at Problem creation (like the reference keeps A in the Problem), not per step.
   roofline       dominant kernel k_gram: n*m*(m+1) flops per launch / mean launch time (CUDA events around every
                  launch, taken inside the timed region) against the FP64 tensor peak measured live with cuBLAS DGEMM.
-  roofline_stream  the HBM-bound forward / adjoint passes: 8*n*m bytes per pass against MEASURED_PEAKS.json hbm_gbs.
+  roofline_stream  the HBM-bound passes over A (k_fused_grad: objective + gradient in one read; k_forward / k_adjoint
+                 where only one of them is needed): 8*n*m bytes per pass against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline   the numpy oracle (a port: julia is not in the image) on the host cores over a bounded row sample.
 """
 from __future__ import annotations
@@ -391,7 +392,7 @@ def main():
         gram_equiv = None
         if g_calls and gram_path == "i8":
             # emulated-fp64 Gram: k_i8syrk runs NMOD int8 SYRKs; algorithmic int8 ops = NMOD * n*m*(m+1)
-            nmod = 15
+            nmod, kept_bits = model.gram_info()
             ops = nmod * float(nl) * m * (m + 1)
             ach = ops / (g_ms / g_calls * 1e-3) / 1e12
             try:
@@ -403,8 +404,8 @@ def main():
             roof = {"bound": "tensor", "kernel": "k_i8syrk (tcgen05.mma kind::i8, TMA multicast, TMEM int32 accumulators)",
                     "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": traffic.get("k_i8syrk"),
                     "peak_source": i8_src, "algorithmic_ops_per_launch": ops, "ms_per_launch": g_ms / g_calls,
-                    "launches_timed": g_calls}
-            tot = (g_ms + stages["fused"][0] + stages["gram_finalize"][0]) / g_calls
+                    "launches_timed": g_calls, "moduli": nmod, "fixed_point_bits": kept_bits}
+            tot = (g_ms + stages["residues"][0] + stages["gram_finalize"][0]) / g_calls
             fe = float(nl) * m * (m + 1) / (tot * 1e-3) / 1e12
             gram_equiv = {"what": "whole emulated-fp64 Gram (residues + int8 SYRK + CRT) as fp64-equivalent throughput",
                           "fp64_equiv_tflops": fe, "ms": tot, "vs_measured_dgemm_peak": fe / peak_sus,
@@ -418,16 +419,18 @@ def main():
                                    f"in this run; burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)",
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": g_ms / g_calls, "launches_timed": g_calls}
         stream = {}
-        for nm, (s_ms, s_calls) in (("forward", (f_ms, f_calls)), ("adjoint", (a_ms, a_calls))):
+        kname = {"forward": "k_forward", "adjoint": "k_adjoint", "fused": "k_fused_grad"}
+        for nm in ("fused", "forward", "adjoint"):
+            s_ms, s_calls = stages[nm]
             if s_calls:
-                by = 8.0 * nl * m
+                by = 8.0 * nl * m  # one read of A: forward z=Ax, adjoint g=A'r, or the fused pass doing both
                 ach = by / (s_ms / s_calls * 1e-3) / 1e9
-                stream[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                              "algorithmic_bytes_per_launch": by, "ms_per_launch": s_ms / s_calls,
-                              "launches_timed": s_calls, "peak_source": peaks_src, "traffic": traffic.get("k_" + nm)}
+                stream[nm] = {"bound": "hbm", "kernel": kname[nm], "achieved": ach, "peak": hbm, "unit": "GB/s",
+                              "frac": ach / hbm, "algorithmic_bytes_per_launch": by, "ms_per_launch": s_ms / s_calls,
+                              "launches_timed": s_calls, "peak_source": peaks_src, "traffic": traffic.get(kname[nm])}
         if roof is None and stream:  # LQN workloads: the streaming pass is the dominant kernel
-            k = "forward" if "forward" in stream else "adjoint"
-            roof = dict(stream[k], kernel="k_" + k)
+            k = next(iter(stream))
+            roof = dict(stream[k])
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(cpu_sample_rows(wl), n_local)

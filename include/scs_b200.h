@@ -113,6 +113,12 @@ int scs_set_L(scs_problem* p, int has_L, double L);
  * scs_get_gram_path reports what the last Gram used (1 = DMMA, 2 = tcgen05 int8). */
 int scs_set_gram_mode(scs_problem* p, int mode);
 int scs_get_gram_path(scs_problem* p, int* path);
+/* Fixed-point precision of the emulated-fp64 Gram: every column of diag(sqrt w) A keeps at least `bits` bits below its
+ * largest entry (24..50, default 40; call before the first Gram).  The library uses the shortest prefix of its 15
+ * moduli that holds the exact integer Gram at that precision.  scs_get_gram_info reports the moduli count and the
+ * bits actually kept (0, 0 before the int8 path has run). */
+int scs_set_gram_bits(scs_problem* p, int bits);
+int scs_get_gram_info(scs_problem* p, int* nmod, int* bits);
 /* Streaming-pass selection for "objective + gradient at the same x": 0 = auto (the single-pass cluster kernel
  * k_fused_grad when m <= 4096, else two passes), 1 = always two passes (k_forward + k_adjoint), 2 = fused, and
  * SCS_UNSUPPORTED if the shape has no fused kernel.  scs_get_stream_path reports what the last gradient used

@@ -6,17 +6,19 @@
 //   1. C = diag(sqrt(w)) A is brought to fixed point per column:  X_ij = rint(C_ij * 2^(b - e_j)),  |X| <= 2^b,
 //      2^e_j >= max_i |C_ij|  (bound: max sqrt(w) * colmax|A|).  Needs w >= 0 (Newton weights, consistent-label
 //      GGN weights, least squares); otherwise the caller stays on the DMMA kernel.
-//   2. k_residues writes, for each of kNMod pairwise-coprime moduli p_l <= 256, the symmetric residue plane
+//   2. k_residues writes, for each of the first nmod (10..15) pairwise-coprime moduli p_l <= 256, the symmetric residue plane
 //      x_l = X mod p_l as int8 (column-major, K = rows contiguous).
 //   3. k_i8syrk computes S_l = x_l' x_l mod p_l on lower-triangle 128x256 tiles with tcgen05.mma.kind::i8
 //      (TMA SWIZZLE_128B operand tiles -> 4-stage mbarrier ring -> UMMA 128x256x32, int32 accumulators in TMEM,
 //      double-buffered), one K chunk (<= 65536 rows: |acc| <= 2^30) at a time; the epilogue warps pull the
 //      accumulator with tcgen05.ld, reduce mod p_l and store int8 partial residues.
 //   4. k_crt sums the chunk residues, reconstructs R = sum_i X_ij X_ik exactly by CRT in 128-bit integers
-//      (P = prod p_l ~ 2^117.8 > 2 n 2^(2b)) and writes G_jk = R * 2^(e_j + e_k - 2b) to both triangles.
+//      (P = prod p_l > 2 n 2^(2b)) and writes G_jk = R * 2^(e_j + e_k - 2b) to both triangles.
 //
-// The only rounding is the fixed-point quantisation of C (b = 48 bits below the column maximum at n = 1e6) and
-// the final conversion to fp64; the integer Gram itself is exact and bit-reproducible.
+// The only rounding is the fixed-point quantisation of C (b bits below the column maximum) and the final conversion
+// to fp64; the integer Gram itself is exact and bit-reproducible.  The host picks the shortest moduli prefix that
+// still gives b >= the requested bits (default 40: a quantisation error of 2^-40 (colmax/rms)/sqrt(n) relative to
+// the diagonal — below the rounding noise of an fp64 DGEMM of the same length; 13 moduli at n = 1e6, b = 48 needs 15).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -135,11 +137,12 @@ __global__ void k_colscale(const double* __restrict__ colmax, const double* __re
 //   r  = fma(-q, p, X)                    exact, |r| <= p/2 (+1 for p = 256 at a tie) -> its low byte is a valid residue
 //   lo32(r + M)                           two's-complement bits of r
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+template <int NMOD>
 __global__ void __launch_bounds__(256)
 k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const double* __restrict__ w,
            const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx) {
-  __shared__ double s_p[kNMod], s_ip[kNMod];
-  if (threadIdx.x < kNMod) {
+  __shared__ double s_p[NMOD], s_ip[NMOD];
+  if (threadIdx.x < NMOD) {
     s_p[threadIdx.x] = (double)c_mod_p[threadIdx.x];
     s_ip[threadIdx.x] = 1.0 / (double)c_mod_p[threadIdx.x];
   }
@@ -166,7 +169,7 @@ k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const do
     }
     int8_t* dst = planes + (int64_t)j * ldx + i0;
 #pragma unroll
-    for (int l = 0; l < kNMod; ++l) {
+    for (int l = 0; l < NMOD; ++l) {
       const double p = s_p[l], ip = s_ip[l];
       uint32_t b[8];
 #pragma unroll
@@ -463,9 +466,10 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ eco
   const int64_t cstride = (int64_t)pl.m * pl.ldp;
   unsigned __int128 acc[4] = {0, 0, 0, 0};
   double frac[4] = {0.0, 0.0, 0.0, 0.0};
+  const int var = pl.nmod - kNModMin;  // which moduli prefix the planes were built with
 #pragma unroll 1
-  for (int l = 0; l < kNMod; ++l) {
-    const int p = c_mod_p[l], ql = c_mod_q[l];
+  for (int l = 0; l < pl.nmod; ++l) {
+    const int p = c_mod_p[l], ql = c_mod_q[var][l];
     const int8_t* src = partial + ((int64_t)l * pl.nchunks * pl.m + jc) * pl.ldp + kc0;
     int s[4] = {0, 0, 0, 0};
     for (int c = 0; c < pl.nchunks; ++c) {
@@ -475,7 +479,7 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ eco
       s[2] += (int)(int8_t)((v >> 16) & 0xff);
       s[3] += (int)(int8_t)(v >> 24);
     }
-    const unsigned __int128 Ml = ((unsigned __int128)c_mod_Mhi[l] << 64) | c_mod_Mlo[l];
+    const unsigned __int128 Ml = ((unsigned __int128)c_mod_Mhi[var][l] << 64) | c_mod_Mlo[var][l];
     const double ipd = 1.0 / (double)p;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -486,7 +490,7 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ eco
       frac[e] += (double)tl * ipd;
     }
   }
-  const unsigned __int128 P = ((unsigned __int128)c_P_hi << 64) | c_P_lo;
+  const unsigned __int128 P = ((unsigned __int128)c_P_hi[var] << 64) | c_P_lo[var];
   const int ej = ecol[jc];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {

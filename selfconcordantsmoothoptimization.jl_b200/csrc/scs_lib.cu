@@ -194,7 +194,7 @@ struct scs_problem {
   int2* d_i8tiles = nullptr;
   unsigned long long* d_i8progress = nullptr;
   int64_t ldx = 0;
-  int i8_b = 0, i8_clusters = 0;
+  int i8_b = 0, i8_clusters = 0, i8_bits = 40, i8_nmod = 0;
   I8Plan i8plan{};
   CUtensorMap xmap{}, xmap_b{};
   // single-pass fused gradient (kernels_fused.cuh)
@@ -519,10 +519,19 @@ static int i8_setup(scs_problem* p) {
   scs_ctx* c = p->ctx;
   const int64_t m = p->m;
   p->ldx = round_up(p->ldd, kI8BK);
-  const size_t plane_bytes = (size_t)kNMod * p->ldx * m;
+  // shortest moduli prefix with P/2 > n * 2^(2b) for b >= the requested bits; b then takes all the headroom of that P
+  int nmod = kNMod;
+  for (int k = kNModMin; k <= kNMod; ++k)
+    if (h_log2P[k - kNModMin] - 1.0 - std::log2((double)p->ldx) >= 2.0 * p->i8_bits) {
+      nmod = k;
+      break;
+    }
+  p->i8_nmod = nmod;
+  p->i8_b = std::min((int)std::floor((h_log2P[nmod - kNModMin] - 1.0 - std::log2((double)p->ldx)) / 2.0), 50);
+  const size_t plane_bytes = (size_t)nmod * p->ldx * m;
   I8Plan& pl = p->i8plan;
   pl.m = (int)m;
-  pl.nmod = kNMod;
+  pl.nmod = nmod;
   pl.kblocks = p->ldx / kI8BK;
   pl.chunk_kblocks = kI8ChunkRows / kI8BK;
   pl.nchunks = (int)((pl.kblocks + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
@@ -536,7 +545,7 @@ static int i8_setup(scs_problem* p) {
       if ((int64_t)bj * kI8BN <= (int64_t)(g + 1) * kI8Cluster * kI8BM - 1) tiles.push_back(make_int2(g, bj));
   pl.ntiles = (int)tiles.size();
   pl.units = (int64_t)pl.nmod * pl.nchunks * pl.ntiles;
-  const size_t partial_bytes = (size_t)kNMod * pl.nchunks * m * pl.ldp;
+  const size_t partial_bytes = (size_t)nmod * pl.nchunks * m * pl.ldp;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   if (plane_bytes + partial_bytes + (2ull << 30) > free_b) {
@@ -555,11 +564,8 @@ static int i8_setup(scs_problem* p) {
   CU_TRY(cudaMalloc((void**)&p->d_i8progress, sizeof(unsigned long long)));
   CU_TRY(cudaMemcpyAsync(p->d_i8tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
-  // P/2 > n * 2^(2b)
-  int b = (int)std::floor((kLog2P - 1.0 - std::log2((double)p->ldx)) / 2.0);
-  p->i8_b = std::min(b, 50);
   if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[3] = {(cuuint64_t)p->ldx, (cuuint64_t)m, (cuuint64_t)kNMod};
+  cuuint64_t gdim[3] = {(cuuint64_t)p->ldx, (cuuint64_t)m, (cuuint64_t)nmod};
   cuuint64_t gstride[2] = {(cuuint64_t)p->ldx, (cuuint64_t)p->ldx * (cuuint64_t)m};
   cuuint32_t box[3] = {(cuuint32_t)kI8BK, 128u, 1u};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -597,8 +603,22 @@ static int run_gram_i8(scs_problem* p, int* done) {
     if (!(st[1] >= 0.0) || !std::isfinite(st[0])) return SCS_OK;  // not eligible
     LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, p->d_colmax, p->d_wstat, m, p->i8_b, p->d_ecol, p->d_colscale);
     const unsigned gx = (unsigned)((p->ldd / 8 + 255) / 256);
-    LAUNCH(c, k_residues, dim3(gx, (unsigned)std::min(m, 64)), 256, 0, p->dA, p->ldd, p->n, m, p->dw, p->d_colscale,
-           p->d_planes, p->ldx);
+    const dim3 rgrid(gx, (unsigned)std::min(m, 64));
+    switch (p->i8_nmod) {
+#define SCS_RES_CASE(K)                                                                                            \
+  case K:                                                                                                          \
+    LAUNCH(c, k_residues<K>, rgrid, 256, 0, p->dA, p->ldd, p->n, m, p->dw, p->d_colscale, p->d_planes, p->ldx);    \
+    break;
+      SCS_RES_CASE(10)
+      SCS_RES_CASE(11)
+      SCS_RES_CASE(12)
+      SCS_RES_CASE(13)
+      SCS_RES_CASE(14)
+      SCS_RES_CASE(15)
+#undef SCS_RES_CASE
+      default:
+        return fail(SCS_STATE_ERROR, "int8 Gram: bad moduli count");
+    }
     p->i8_planes_valid = true;
   }
   {
@@ -1148,6 +1168,19 @@ extern "C" int scs_set_stream_mode(scs_problem* p, int mode) {
 extern "C" int scs_get_stream_path(scs_problem* p, int* path) {
   if (!p || !path) return fail(SCS_INVALID_ARG, "NULL argument");
   *path = p->last_stream_path;
+  return SCS_OK;
+}
+extern "C" int scs_set_gram_bits(scs_problem* p, int bits) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (bits < 24 || bits > 50) return fail(SCS_INVALID_ARG, "gram bits must be in 24..50");
+  if (p->i8_ready) return fail(SCS_STATE_ERROR, "scs_set_gram_bits must be called before the first Gram");
+  p->i8_bits = bits;
+  return SCS_OK;
+}
+extern "C" int scs_get_gram_info(scs_problem* p, int* nmod, int* bits) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (nmod) *nmod = p->i8_nmod;
+  if (bits) *bits = p->i8_b;
   return SCS_OK;
 }
 extern "C" int scs_get_gram_path(scs_problem* p, int* path) {

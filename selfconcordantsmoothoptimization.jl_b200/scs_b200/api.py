@@ -311,6 +311,16 @@ class Problem:
         K.check(K.lib().scs_get_gram_path(self._h, C.byref(v)))
         return {0: None, 1: "dmma", 2: "i8"}[v.value]
 
+    def set_gram_bits(self, bits):
+        """Fixed-point bits kept below each column's largest entry by the emulated-fp64 Gram (24..50, default 40)."""
+        K.check(K.lib().scs_set_gram_bits(self._h, int(bits)))
+
+    def gram_info(self):
+        """(moduli used, bits kept) by the emulated-fp64 Gram; (0, 0) before it has run."""
+        a, b = C.c_int(), C.c_int()
+        K.check(K.lib().scs_get_gram_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_stream_mode(self, mode):
         """"auto" | "two_pass" | "fused": how objective + gradient at the same x read A (once or twice)."""
         K.check(K.lib().scs_set_stream_mode(self._h, {"auto": 0, "two_pass": 1, "fused": 2}[mode]))

@@ -257,13 +257,18 @@ def test_synthetic_generator_bits(scs):
 
 # ---- emulated-fp64 Gram on tcgen05 int8 (kernels_i8gram.cuh) ------------------------------------------------
 @pytest.mark.parametrize("n,m", [(5, 2), (100, 50), (513, 130), (3001, 257), (4096, 512), (70001, 300), (131072 + 77, 640)])
-def test_gram_i8_matches_fp64(scs, n, m):
+@pytest.mark.parametrize("bits", [None, 30, 48])
+def test_gram_i8_matches_fp64(scs, n, m, bits):
     """Forced int8/CRT path vs the fp64 oracle Gram.  The integer Gram is exact; the only error is the fixed-point
-    quantisation of sqrt(w)*A (>= 48 bits below the column maximum), so entries agree to ~1e-13 of the diagonal scale.
-    n > 65536 exercises several K chunks, m not a multiple of 128/256 the ragged tiles."""
+    quantisation of sqrt(w)*A (default: >= 40 bits below the column maximum), so entries agree to ~1e-13 of the
+    diagonal scale.  n > 65536 exercises several K chunks, m not a multiple of 128/256 the ragged tiles; the
+    requested bits select the moduli prefix (10..15 moduli)."""
     A, y, x = logistic_problem(n, m)
     p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "consistent"), 0.1)
     p.set_gram_mode("i8")
+    if bits:
+        p.set_gram_bits(bits)
+    tol = 2e-12 if bits != 30 else 2e-9
     Lo = O.LogisticLoss(1 / n, "consistent")
     z = A @ x
     for wk in ("newton", "ggn"):
@@ -273,7 +278,14 @@ def test_gram_i8_matches_fp64(scs, n, m):
         Gref = A.T @ (w[:, None] * A)
         assert np.array_equal(G, G.T)
         d = np.sqrt(np.diag(Gref))
-        assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 2e-12
+        assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= tol
+        nmod, kept = p.gram_info()
+        assert kept >= (bits or 40) and 10 <= nmod <= 15
+        ldx = -(-(-(-n // 16) * 16) // 128) * 128  # rows padded to 16, then to the 128-row K block
+        need = 2 * (bits or 40) + np.log2(ldx) + 1
+        assert nmod == 10 or need > [79.24, 87.04, 94.80, 102.52, 110.16][nmod - 11]  # shortest sufficient prefix
+    with pytest.raises(scs.ScsError):
+        p.set_gram_bits(44)  # planes already laid out
     # negative weights (literal +-1 labels, GGN): not eligible -> the DMMA kernel must take over
     p2 = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "literal"), 0.1)
     p2.set_gram_mode("i8")
