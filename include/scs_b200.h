@@ -24,7 +24,9 @@
  *   scs_objective           model.f(model.A, model.y, x), get_reg(model,x,reg_name)   iterate.jl:168,189-190
  *   scs_step                step!(method, model, reg_name, hμ, As, x, x_prev, ys, Cmat, iter; return_dx)
  *                                                                           iterate.jl:52-54,233; prox-*-SCORE.jl step!
- *   scs_solve               optim_loop!(method, model, reg_name, hμ; opt)   iterate.jl:100-266 (full-batch)
+ *   scs_solve               optim_loop!(method, model, reg_name, hμ; opt)   iterate.jl:100-266
+ *   scs_set_batches /       get_data_loader / get_loader_subset / the inner `for (i, sample) in enumerate(data)`
+ *   scs_set_active_rows                                                     iterate.jl:139-145,204-207, utils.jl:14-25
  *   scs_loss_eval           f / gradient(f,x) / out_fn pieces               prox-N-SCORE.jl:49-69, prox-GGN-SCORE.jl:44-56
  *   scs_gram                hessian(f,x) | Jt*Q*Jt'                         prox-N-SCORE.jl:63, prox-GGN-SCORE.jl:129
  *   scs_linear_solve        (H + λHr) \ ∇q | qr(JQJ) \ Je                   prox-N-SCORE.jl:70, prox-GGN-SCORE.jl:131
@@ -119,6 +121,15 @@ int scs_get_gram_path(scs_problem* p, int* path);
  * bits actually kept (0, 0 before the int8 path has run). */
 int scs_set_gram_bits(scs_problem* p, int bits);
 int scs_get_gram_info(scs_problem* p, int* nmod, int* bits);
+/* Mini-batches (optim_loop!'s data loader, iterate.jl:139-145,204-207; utils.jl:18-25).  The host lays the rows of a
+ * shard out batch after batch (after its one-time shuffle, if any); a batch is then a contiguous local row range.
+ * scs_set_active_rows restricts every following pass (scs_step, scs_loss_eval, scs_gram, and scs_objective — the
+ * host resets it to [0, n_local) for the objective, which the reference always takes over the whole data) to rows
+ * [row_lo, row_hi) of the shard; any bounds are accepted, the kernels sweep the 128-row-aligned superset and mask.
+ * scs_set_batches gives scs_solve the table of nbatch+1 local offsets it steps through every epoch (nbatch = 0:
+ * full batch).  With several ranks every rank passes its own offsets for the same nbatch batches. */
+int scs_set_active_rows(scs_problem* p, int64_t row_lo, int64_t row_hi);
+int scs_set_batches(scs_problem* p, int64_t nbatch, const int64_t* offsets);
 /* Streaming-pass selection for "objective + gradient at the same x": 0 = auto (the single-pass cluster kernel
  * k_fused_grad when m <= 4096, else two passes), 1 = always two passes (k_forward + k_adjoint), 2 = fused, and
  * SCS_UNSUPPORTED if the shape has no fused kernel.  scs_get_stream_path reports what the last gradient used

@@ -684,7 +684,7 @@ class ProxLQNSCORE:  # prox-L-BFGS-SCORE.jl:6-30
 
 
 # --------------------------------------------------------------------------------------
-# Driver (src/algorithms/iterate.jl:56-76, 100-266), full-batch only
+# Driver (src/algorithms/iterate.jl:56-76, 100-266): full batch, mini-batches, slice_samples
 # --------------------------------------------------------------------------------------
 @dataclass
 class Solution:  # iterate.jl:3-32
@@ -702,9 +702,55 @@ def _norm(v):
     return float(np.linalg.norm(v))
 
 
-def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-10, f_tol=1e-10):
+def make_batches(n, batch_size=None, slice_samples=False, shuffle_batch=False, local_max_iter=None, perm=None):
+    """Row index sets of the batches optim_loop! iterates over (iterate.jl:122-145, utils.jl:14-25).
+
+    MLUtils.DataLoader(batchsize=b, shuffle, partial=true) over n observations: ceil(n/b) consecutive batches of the
+    (once) shuffled order, the last one possibly short.  `collect(loader)` runs the loader ONCE before the epoch
+    loop, so the same batches are reused in every epoch.  slice_samples (one row per step) yields to batch_size when
+    both are given (:127-130).  local_max_iter keeps only the first min(floor(local_max_iter), max_iter) batches
+    (:124,:127,:145).  The shuffle is Julia's RNG upstream; here the permutation is an explicit input (`perm`) so
+    that the oracle and the GPU path see the same batches."""
+    if batch_size is not None and slice_samples:
+        slice_samples = False
+    if slice_samples:
+        batch_size = 1
+        shuffle_batch = False
+    if batch_size is None:
+        batch_size = n
+        shuffle_batch = False
+    batch_size = int(batch_size)
+    order = np.arange(n)
+    if shuffle_batch:
+        if perm is None:
+            raise ValueError("shuffle_batch needs an explicit permutation (perm=) in this restatement")
+        order = np.asarray(perm, dtype=np.int64)
+        assert sorted(order.tolist()) == list(range(n))
+    max_iter = -(-n // batch_size)
+    iend = max_iter
+    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
+        iend = min(int(np.floor(local_max_iter)), max_iter)
+    return [order[i * batch_size:min((i + 1) * batch_size, n)] for i in range(iend)]
+
+
+def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-10, f_tol=1e-10, batch_size=None,
+            slice_samples=False, shuffle_batch=False, local_max_iter=None, perm=None):
+    import copy
     if alpha is not None:  # iterate.jl:113-115
         model.L = 1 / alpha
+    n = model.A.shape[0]
+    batches = make_batches(n, batch_size, slice_samples, shuffle_batch, local_max_iter, perm)
+    full = len(batches) == 1 and len(batches[0]) == n and not shuffle_batch
+    views = []
+    for idx in batches:  # As = Matrix(As'), ys = vec(ys') (:206-207): the batch rows as their own problem data
+        if full:
+            views.append(model)
+        else:
+            bm = copy.copy(model)
+            bm.A = np.ascontiguousarray(model.A[idx])
+            bm.y = model.y[idx]
+            views.append(bm)
+    iend = len(batches)
     f = lambda v: model.f.f(model.A, model.y, v)
     objs, fvals, pris, rels, frels, iterates = [], [], [], [], [], []
     epochs = 0
@@ -729,35 +775,29 @@ def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-1
     def push(obj, fval, pri, rel, fr):  # utils.jl:106-113
         objs.append(obj), fvals.append(fval), pris.append(pri), rels.append(rel), frels.append(fr)
 
-    for epoch_t in range(1, max_epoch + 1):  # :185
+    def stats(v):
         with np.errstate(all="ignore"):
-            fval = float(f(x))
-            obj = fval + float(get_reg(model, x, reg_name))
-        rel_error = rel_err(x)
-        f_rel_error = frel(obj)
+            fval = float(f(v))
+            obj = fval + float(get_reg(model, v, reg_name))
+        return obj, fval, rel_err(v), frel(obj)
+
+    for epoch_t in range(1, max_epoch + 1):  # :185
+        obj, fval, rel_error, f_rel_error = stats(x)
         push(obj, fval, pri_res_norm, rel_error, f_rel_error)  # :202
-        # --- single full batch (i == iend == 1), :204-255
-        if epoch_t == max_epoch:  # :219-231: second push of the same pre-step state (quirk 2)
-            with np.errstate(all="ignore"):
-                fval = float(f(x))
-                obj = fval + float(get_reg(model, x, reg_name))
-            rel_error = rel_err(x)
-            f_rel_error = frel(obj)
-            push(obj, fval, pri_res_norm, rel_error, f_rel_error)
-        x_new, pri_res_norm = method.step(model, reg_name, hmu, x, x_prev, Cmat, epoch_t)  # :233
-        iterates.append(x_new.copy())
-        if _norm(x_new - x) < x_tol * max(_norm(x), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :234
-            if epoch_t != max_epoch:  # :235-247 (one extra entry for x_new; refreshes f_rel_error)
-                with np.errstate(all="ignore"):
-                    fval = float(f(x_new))
-                    obj = fval + float(get_reg(model, x_new, reg_name))
-                rel_error = rel_err(x_new)
-                f_rel_error = frel(obj)
+        for i, bm in enumerate(views, start=1):  # :204
+            if epoch_t == max_epoch and i == iend:  # :219-231: stats of the current x once more (quirk 2)
+                obj, fval, rel_error, f_rel_error = stats(x)
                 push(obj, fval, pri_res_norm, rel_error, f_rel_error)
-            x_prev = x.copy()  # :248-251 (then `break`s the one-trip inner loop)
-            x = x_new
-            epochs += 1
-        else:
+            x_new, pri_res_norm = method.step(bm, reg_name, hmu, x, x_prev, Cmat, epoch_t)  # :233
+            iterates.append(x_new.copy())
+            if _norm(x_new - x) < x_tol * max(_norm(x), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :234
+                if epoch_t != max_epoch:  # :235-247 (one extra entry for x_new; refreshes f_rel_error)
+                    obj, fval, rel_error, f_rel_error = stats(x_new)
+                    push(obj, fval, pri_res_norm, rel_error, f_rel_error)
+                x_prev = x.copy()  # :248-251
+                x = x_new
+                epochs += 1
+                break
             x_prev = x.copy()  # :253-254
             x = x_new
         if _norm(x - x_prev) < x_tol * max(_norm(x_prev), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :257

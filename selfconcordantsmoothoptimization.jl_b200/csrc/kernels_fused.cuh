@@ -26,6 +26,8 @@
 //   warp 10    loss warp, for the panels this CTA owns: z_i = sum over ranks in rank order, r_i first (it is on the
 //              critical path) and st.async of r to rs[slot] of every CTA (complete_tx on their rbar[slot]); then the
 //              loss term, w_i and the z / r / w rows to global memory.
+// The kernel works on the row window [row_base, row_base + 16*npanels) of the shard (row_base a multiple of 32); rows
+// outside [win_lo, win_hi) get r = w = z = 0 (padding, or rows of another mini-batch).
 // Rotating the owner spreads the exp/log work over the cluster.  No atomics anywhere: per-cluster partial g and
 // per-CTA loss sums are reduced by k_colsum / k_sum_partials in fixed order => bit-reproducible for a given grid.
 #pragma once
@@ -139,7 +141,8 @@ SCS_DEVINL double loss_r_only(const LossParams& lp, double z, double y) {
 template <bool PROF>
 __global__ void __launch_bounds__(kFuThreads, 1)
 k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict__ x, const double* __restrict__ y,
-             LossParams lp, int64_t n, int64_t npanels, int m, double* __restrict__ z_out, double* __restrict__ r_out,
+             LossParams lp, int64_t row_base, int64_t win_lo, int64_t win_hi, int64_t npanels, int m,
+             double* __restrict__ z_out, double* __restrict__ r_out,
              double* __restrict__ w_out, double* __restrict__ loss_part /* [gridDim.x] */,
              double* __restrict__ gpart /* [clusters][m] */, long long* __restrict__ prof, int dbg_mode) {
   const long long k_t0 = PROF ? clock64() : 0;
@@ -313,7 +316,7 @@ k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict_
           fu_wait(sm_empty + 8u * s, ph);
           if (PROF) c_a += clock64() - w0;
           fu_expect_tx(sm_full + 8u * s, (uint32_t)kFuStageBytes);
-          const int row0 = (int)((cid + (int64_t)u * ncl) * kFuStageRows);
+          const int row0 = (int)(row_base + (cid + (int64_t)u * ncl) * kFuStageRows);
           fu_tma_2d(sm_tiles + (uint32_t)(s * kFuStageBytes), &amap, sm_full + 8u * s, row0, col0);
           fu_tma_2d(sm_tiles + (uint32_t)(s * kFuStageBytes + kFuStageBytes / 2), &amap, sm_full + 8u * s, row0,
                     col0 + kFuBoxCols);
@@ -352,8 +355,8 @@ k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict_
       uint32_t used = 0;  // bit q = parity of zbar[q]'s next phase on this CTA
       for (int t = (int)crank; t < cnt; t += (int)csize) {
         const uint32_t slot = (uint32_t)t & (kFuSlots - 1);
-        const int64_t row = panel_of(t) * kFuRows + (lane & 15);
-        const double yv = y[row];  // y has ldd >= 16*npanels entries (zero padded)
+        const int64_t row = row_base + panel_of(t) * kFuRows + (lane & 15);
+        const double yv = y[row];  // row < row_base + 16*npanels <= ldd (y is zero padded up to ldd)
         if (lane == 0) fu_expect_tx(sm_zbar + 8u * slot, csize * (uint32_t)(kFuRows * 8));
         const long long w0 = PROF ? clock64() : 0;
         fu_wait(sm_zbar + 8u * slot, (used >> slot) & 1u);
@@ -364,7 +367,7 @@ k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict_
           const uint32_t zr = sm_zx + slot * (uint32_t)(kFuMaxCluster * 128) + (uint32_t)(lane * 8);
           double z = lds_f64u(zr);
           for (uint32_t pr = 1; pr < csize; ++pr) z += lds_f64u(zr + pr * 128u);
-          const bool pad = row >= n;  // padding rows: A and y are zero there
+          const bool pad = row < win_lo || row >= win_hi;  // padding rows, or rows of another mini-batch
           const double r = pad ? 0.0 : loss_r_only(lp, z, yv);
           const uint32_t dst = sm_rs + slot * 128u + (uint32_t)(lane * 8), bar = sm_rbar + 8u * slot;
           for (uint32_t pr = 0; pr < csize; ++pr) st_async_f64(mapa_u32(dst, pr), r, mapa_u32(bar, pr));

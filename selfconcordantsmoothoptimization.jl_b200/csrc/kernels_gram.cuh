@@ -95,6 +95,7 @@ SCS_DEVINL void tri_decode(int t, int& bi, int& bj) {
 
 __global__ void __launch_bounds__(kGThreads, 1)
 k_gram(const __grid_constant__ CUtensorMap amap, const double* __restrict__ w, int m, int ldp, GramPlan plan,
+       int64_t kt0 /* first 16-row k-tile of the active row window */,
        double* __restrict__ partial /* [splits][m*ldp], element (jc,kc) at jc*ldp+kc */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,9 +131,9 @@ k_gram(const __grid_constant__ CUtensorMap amap, const double* __restrict__ w, i
         for (int64_t kt = k0; kt < k1; ++kt) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], bytes);
-          tma_load_2d(tilesA + stage * kGTileBytes, &amap, &full[stage], (int)(kt * kGBK), bi * kGT);
-          if (!diag) tma_load_2d(tilesB + stage * kGTileBytes, &amap, &full[stage], (int)(kt * kGBK), bj * kGT);
-          bulk_load_1d(wt + stage * kGBK, w + kt * kGBK, kGBK * 8, &full[stage]);
+          tma_load_2d(tilesA + stage * kGTileBytes, &amap, &full[stage], (int)((kt0 + kt) * kGBK), bi * kGT);
+          if (!diag) tma_load_2d(tilesB + stage * kGTileBytes, &amap, &full[stage], (int)((kt0 + kt) * kGBK), bj * kGT);
+          bulk_load_1d(wt + stage * kGBK, w + (kt0 + kt) * kGBK, kGBK * 8, &full[stage]);
           if (++stage == kGStages) {
             stage = 0;
             phase ^= 1;

@@ -55,7 +55,8 @@ struct I8Plan {
   int nmod;
   int nchunks;
   int ntiles;             // tile groups: kI8Cluster vertically adjacent 128x256 tiles that share one B slab
-  int64_t kblocks;        // ldx / 128
+  int64_t kb_lo;          // first 128-row k-block of the active row window
+  int64_t kblocks;        // one past its last k-block (<= ldx / 128)
   int64_t chunk_kblocks;  // kI8ChunkRows / 128
   int64_t units;          // nmod * nchunks * ntiles
   int ldp;                // bytes per row of a partial-residue matrix
@@ -139,7 +140,7 @@ __global__ void k_colscale(const double* __restrict__ colmax, const double* __re
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 template <int NMOD>
 __global__ void __launch_bounds__(256)
-k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const double* __restrict__ w,
+k_residues(const double* __restrict__ A, int64_t ldd, int64_t nproc, int m, const double* __restrict__ w,
            const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx) {
   __shared__ double s_p[NMOD], s_ip[NMOD];
   if (threadIdx.x < NMOD) {
@@ -148,7 +149,7 @@ k_residues(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const do
   }
   __syncthreads();
   const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-  if (i0 >= ldd) return;  // ldd is a multiple of 16 and rows >= n hold zeros (w too)
+  if (i0 >= nproc) return;  // nproc is a multiple of 8; rows outside the active window have w = 0
   double sw[8];
 #pragma unroll
   for (int q = 0; q < 8; q += 2) {
@@ -324,7 +325,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
         int l = 0, c = 0, t = 0;
         if (valid) i8_unit(pl, u, l, c, t);
         const int2 tile = valid ? tiles[t] : make_int2(0, 0);
-        const int64_t kb0 = (int64_t)c * pl.chunk_kblocks;
+        const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         for (int sg = 0; sg < segs; ++sg) {
           const unsigned long long point = (unsigned long long)(st * segs + sg);
@@ -373,7 +374,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
       for (int64_t u = cid; u < pl.units; u += ncl) {
         int l, c, t;
         i8_unit(pl, u, l, c, t);
-        const int64_t kb0 = (int64_t)c * pl.chunk_kblocks;
+        const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         mbar_wait(&acc_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();

@@ -58,17 +58,19 @@ constexpr int kFwdThreads = 256;
 constexpr int kFwdRows = 2 * kFwdThreads;  // rows per CTA
 constexpr int kXChunk = 2048;              // columns of x staged in shared memory at a time (16 KB)
 
-// z = A x, then loss pieces.  Grid: ceil(n / 512) CTAs of 256 threads.
-// loss_part[blockIdx.x] = sum of this CTA's loss terms (masked to rows < n).
+// z = A x, then loss pieces.  Grid: ceil(nproc / 512) CTAs of 256 threads.
+// Rows [0, nproc) of the (row-window) base pointers are processed (nproc even); rows outside [row_lo, row_hi) are
+// padding or belong to other mini-batches: their z, r, w are written as zeros and they add nothing to the loss.
+// loss_part[blockIdx.x] = sum of this CTA's loss terms.
 template <int UNR>
 __global__ void __launch_bounds__(kFwdThreads)
-k_forward(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const double* __restrict__ x,
-          const double* __restrict__ y, LossParams lp, double* __restrict__ z_out, double* __restrict__ r_out,
-          double* __restrict__ w_out, double* __restrict__ loss_part) {
+k_forward(const double* __restrict__ A, int64_t ldd, int64_t nproc, int64_t row_lo, int64_t row_hi, int m,
+          const double* __restrict__ x, const double* __restrict__ y, LossParams lp, double* __restrict__ z_out,
+          double* __restrict__ r_out, double* __restrict__ w_out, double* __restrict__ loss_part) {
   __shared__ double xs[kXChunk];
   __shared__ double red[32];
   const int64_t i0 = ((int64_t)blockIdx.x * kFwdThreads + threadIdx.x) * 2;
-  const bool active = i0 < n;
+  const bool active = i0 < nproc;
   const double* Ap = A + (active ? i0 : 0);
   // four independent accumulators per row: shorter dependency chains, tighter rounding than one chain
   double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
@@ -101,19 +103,16 @@ k_forward(const double* __restrict__ A, int64_t ldd, int64_t n, int m, const dou
   }
   double part = 0.0;
   if (active) {
-    const double z0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
-    const double z1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    double z0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    double z1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
     const double2 yy = *reinterpret_cast<const double2*>(y + i0);
     double t0, r0, w0, t1, r1, w1;
     loss_row(lp, z0, yy.x, t0, r0, w0);
     loss_row(lp, z1, yy.y, t1, r1, w1);
-    if (i0 + 1 >= n) {  // odd n: the second row is padding
-      t1 = 0.0;
-      r1 = 0.0;
-      w1 = 0.0;
-    }
+    if (i0 < row_lo || i0 >= row_hi) t0 = r0 = w0 = z0 = 0.0;
+    if (i0 + 1 < row_lo || i0 + 1 >= row_hi) t1 = r1 = w1 = z1 = 0.0;
     part = t0 + t1;
-    if (z_out) *reinterpret_cast<double2*>(z_out + i0) = make_double2(z0, i0 + 1 < n ? z1 : 0.0);
+    if (z_out) *reinterpret_cast<double2*>(z_out + i0) = make_double2(z0, z1);
     if (r_out) *reinterpret_cast<double2*>(r_out + i0) = make_double2(r0, r1);
     if (w_out) *reinterpret_cast<double2*>(w_out + i0) = make_double2(w0, w1);
   }
@@ -131,21 +130,21 @@ __global__ void __launch_bounds__(kVecThreads) k_sum_partials(const double* __re
   if (threadIdx.x == 0) out[0] = s;
 }
 
-// g = A' r.  CTA b owns the 64*K rows [b*64K, (b+1)*64K); warp w sweeps columns w, w+8, ...; lane l keeps
+// g = A' r over rows [0, nproc) of the base pointers (ldd = column stride).  CTA b owns the 64*K rows [b*64K, (b+1)*64K); warp w sweeps columns w, w+8, ...; lane l keeps
 // r for rows base + 2l + 64k (+1) in registers.  part[b*m + j] = this row block's contribution to g_j.
 constexpr int kAdjThreads = 256;
 constexpr int kAdjWarps = kAdjThreads / 32;
 
 template <int K>
 __global__ void __launch_bounds__(kAdjThreads)
-k_adjoint(const double* __restrict__ A, int64_t ldd, int m, const double* __restrict__ r,
+k_adjoint(const double* __restrict__ A, int64_t ldd, int64_t nproc, int m, const double* __restrict__ r,
           double* __restrict__ part) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = (int64_t)blockIdx.x * (64 * K) + 2 * lane;
-  // rows are valid while < ldd (ldd is even; rows in [n, ldd) hold zeros in A and r)
+  // rows are valid while < nproc (even; padding rows hold zeros in A, rows outside the active window zeros in r)
   int nk = 0;
-  if (base < ldd) {
-    const int64_t q = (ldd - base + 63) / 64;
+  if (base < nproc) {
+    const int64_t q = (nproc - base + 63) / 64;
     nk = q < (int64_t)K ? (int)q : K;
   }
   double2 rr[K];
@@ -154,7 +153,7 @@ k_adjoint(const double* __restrict__ A, int64_t ldd, int m, const double* __rest
     rr[k] = k < nk ? *reinterpret_cast<const double2*>(r + base + 64 * k) : make_double2(0.0, 0.0);
   const bool full = __all_sync(0xffffffffu, nk == K);
   double* out = part + (int64_t)blockIdx.x * m;
-  const double* Ab = A + (base < ldd ? base : 0);
+  const double* Ab = A + (base < nproc ? base : 0);
   if (full) {
     int j = warp;
     for (; j + kAdjWarps < m; j += 2 * kAdjWarps) {  // two columns in flight per warp

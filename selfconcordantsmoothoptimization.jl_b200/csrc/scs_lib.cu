@@ -153,6 +153,12 @@ struct DevBuf {
 struct scs_problem {
   scs_ctx* ctx = nullptr;
   int64_t n = 0, m = 0, ldd = 0, mp = 0;  // mp = m rounded up to 16 (padded vector length)
+  // active row window (mini-batches, iterate.jl:204-207): rows [win_lo, win_hi) of the shard take part in the passes;
+  // kernels sweep the 128-row-aligned superset [alo, ahi) and mask the rest.  Default: the whole shard.
+  int64_t win_lo = 0, win_hi = 0, alo = 0, ahi = 0;
+  int64_t win_rows_global = 0;  // rows of the window summed over ranks
+  std::vector<int64_t> batch_off;  // local offsets of the mini-batches scs_solve iterates over (empty: full batch)
+  std::vector<int64_t> batch_rows_global;  // rows of each batch summed over ranks; last entry: the whole problem
   double *dA = nullptr, *dy = nullptr, *dz = nullptr, *dr = nullptr, *dw = nullptr;
   LossParams loss{};
   // regulariser / smoother
@@ -233,6 +239,9 @@ struct XRef {
 static int dalloc(double** p, size_t n) {
   CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)));
   CU_TRY(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(double)));
+  // the memset runs on the legacy default stream, which the contexts' non-blocking streams do not wait for: finish it
+  // before anything is queued on them (set-up path only)
+  CU_TRY(cudaStreamSynchronize(0));
   return SCS_OK;
 }
 static void dfree(void* p) {
@@ -249,16 +258,52 @@ static int run_forward(scs_problem* p, const double* dx, int wk) {
   StageTimer t(c, ST_FWD);
   LossParams lp = p->loss;
   lp.weight_kind = wk;
-  LAUNCH(c, k_forward<8>, (unsigned)p->fwd_blocks, kFwdThreads, 0, p->dA, p->ldd, p->n, (int)p->m, dx, p->dy, lp,
-         p->dz, p->dr, p->dw, p->d_losspart);
-  LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_losspart, p->fwd_blocks, p->d_gl + p->m);
+  const int64_t nproc = p->ahi - p->alo;
+  const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
+  if (blocks > 0)
+    LAUNCH(c, k_forward<8>, (unsigned)blocks, kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc, p->win_lo - p->alo,
+           p->win_hi - p->alo, (int)p->m, dx, p->dy + p->alo, lp, p->dz + p->alo, p->dr + p->alo, p->dw + p->alo,
+           p->d_losspart);
+  LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_losspart, blocks, p->d_gl + p->m);
   return SCS_OK;
 }
 static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
   scs_ctx* c = p->ctx;
   StageTimer t(c, ST_ADJ);
-  LAUNCH(c, k_adjoint<8>, (unsigned)p->adj_blocks, kAdjThreads, 0, p->dA, p->ldd, (int)p->m, dr, p->d_adjpart);
-  LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_adjpart, p->adj_blocks, (int)p->m, dout);
+  const int64_t nproc = p->ahi - p->alo;
+  const int64_t blocks = (nproc + 64 * 8 - 1) / (64 * 8);
+  if (blocks > 0)
+    LAUNCH(c, k_adjoint<8>, (unsigned)blocks, kAdjThreads, 0, p->dA + p->alo, p->ldd, nproc, (int)p->m, dr + p->alo,
+           p->d_adjpart);
+  LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_adjpart, blocks, (int)p->m, dout);
+  return SCS_OK;
+}
+
+static int allreduce(scs_ctx* c, double* buf, size_t count);
+// Select the rows that take part in the following passes.  Everything cached for the previous window is dropped.
+static int set_window(scs_problem* p, int64_t lo, int64_t hi, int64_t rows_global = -1) {
+  if (lo < 0 || hi < lo || hi > p->n) return fail(SCS_INVALID_ARG, "row window outside the shard");
+  if (lo == p->win_lo && hi == p->win_hi && p->win_rows_global > 0) return SCS_OK;
+  p->win_lo = lo;
+  p->win_hi = hi;
+  p->alo = lo / 128 * 128;
+  p->ahi = hi > lo ? std::min(round_up(hi, 128), p->ldd) : p->alo;
+  p->fwd_id = 0;
+  p->grad_id = 0;
+  p->gq_id = 0;
+  p->gqprev_id = 0;
+  p->loss_reduced = false;
+  p->i8_planes_valid = false;
+  p->win_rows_global = rows_global >= 0 ? rows_global : hi - lo;
+  if (p->ctx->world > 1 && rows_global < 0) {  // the GGN wide-branch test needs the global batch size
+    const double v = (double)(hi - lo);
+    CU_TRY(cudaMemcpyAsync(p->d_scal + SC_COUNT - 1, &v, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    SCS_TRY(allreduce(p->ctx, p->d_scal + SC_COUNT - 1, 1));
+    double tot = 0;
+    CU_TRY(cudaMemcpyAsync(&tot, p->d_scal + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+    p->win_rows_global = (int64_t)(tot + 0.5);
+  }
   return SCS_OK;
 }
 
@@ -342,8 +387,8 @@ static int run_fused(scs_problem* p, const double* dx, int wk) {
   StageTimer t(c, ST_FUSED);
   LossParams lp = p->loss;
   lp.weight_kind = wk;
-  const int64_t npanels = p->ldd / kFuRows;
-  const int ncl = (int)std::min<int64_t>(p->fu_clusters, (npanels + 1) / 2);
+  const int64_t npanels = (p->ahi - p->alo) / kFuRows;
+  const int ncl = (int)std::max<int64_t>(1, std::min<int64_t>(p->fu_clusters, (npanels + 1) / 2));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fused_config(p, &cfg, attr, ncl);
@@ -353,8 +398,8 @@ static int run_fused(scs_problem* p, const double* dx, int wk) {
     const size_t np = (size_t)cfg.gridDim.x * 8;
     CU_TRY(cudaMalloc((void**)&dprof, np * sizeof(long long)));
     CU_TRY(cudaMemsetAsync(dprof, 0, np * sizeof(long long), c->stream));
-    le = cudaLaunchKernelEx(&cfg, k_fused_grad<true>, p->fumap, dx, (const double*)p->dy, lp, p->n, npanels, (int)p->m,
-                            p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, dprof, atoi(getenv("SCS_FUSED_PROF")) == 2 ? 1 : 0);
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<true>, p->fumap, dx, (const double*)p->dy, lp, p->alo, p->win_lo,
+                            p->win_hi, npanels, (int)p->m, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, dprof, atoi(getenv("SCS_FUSED_PROF")) == 2 ? 1 : 0);
     std::vector<long long> h(np);
     cudaMemcpyAsync(h.data(), dprof, np * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -370,8 +415,9 @@ static int run_fused(scs_problem* p, const double* dx, int wk) {
             ncl, p->fu_cluster, panels, s[0] / nb, s[0] / nb / panels, s[1] / nb, s[2] / nb, s[7] / nb, s[3] / nb,
             s[4] / nb, s[5] / nb, s[6] / nb);
   } else {
-    le = cudaLaunchKernelEx(&cfg, k_fused_grad<false>, p->fumap, dx, (const double*)p->dy, lp, p->n, npanels, (int)p->m,
-                            p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, (long long*)nullptr, 0);
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<false>, p->fumap, dx, (const double*)p->dy, lp, p->alo, p->win_lo,
+                            p->win_hi, npanels, (int)p->m, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart,
+                            (long long*)nullptr, 0);
   }
   c->launches += 1;
   if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_fused_grad launch: ") + cudaGetErrorString(le));
@@ -532,6 +578,7 @@ static int i8_setup(scs_problem* p) {
   I8Plan& pl = p->i8plan;
   pl.m = (int)m;
   pl.nmod = nmod;
+  pl.kb_lo = 0;
   pl.kblocks = p->ldx / kI8BK;
   pl.chunk_kblocks = kI8ChunkRows / kI8BK;
   pl.nchunks = (int)((pl.kblocks + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
@@ -593,21 +640,30 @@ static int run_gram_i8(scs_problem* p, int* done) {
   *done = 0;
   SCS_TRY(i8_setup(p));
   const int m = (int)p->m;
-  const bool const_w = p->loss.kind == SCS_LOSS_LEASTSQUARES;  // w = 1/denominator: planes never change
+  // least squares: w = 1/denominator on every row, so the planes of the whole shard never change
+  const bool const_w = p->loss.kind == SCS_LOSS_LEASTSQUARES && p->win_lo == 0 && p->win_hi == p->n;
+  const int64_t nproc = p->ahi - p->alo;
+  if (nproc <= 0) return SCS_OK;  // empty window: the DMMA path writes the zero Gram
+  I8Plan pl = p->i8plan;  // restricted to the active row window
+  pl.kb_lo = p->alo / kI8BK;
+  pl.kblocks = pl.kb_lo + (nproc + kI8BK - 1) / kI8BK;
+  pl.nchunks = (int)((pl.kblocks - pl.kb_lo + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
+  pl.units = (int64_t)pl.nmod * pl.nchunks * pl.ntiles;
   if (!(const_w && p->i8_planes_valid)) {
     StageTimer t(c, ST_RESID);
-    LAUNCH(c, k_wstat, 1, kVecThreads, 0, p->dw, p->n, p->d_wstat);
+    LAUNCH(c, k_wstat, 1, kVecThreads, 0, p->dw + p->alo, nproc, p->d_wstat);
     double st[2];
     CU_TRY(cudaMemcpyAsync(st, p->d_wstat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (!(st[1] >= 0.0) || !std::isfinite(st[0])) return SCS_OK;  // not eligible
     LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, p->d_colmax, p->d_wstat, m, p->i8_b, p->d_ecol, p->d_colscale);
-    const unsigned gx = (unsigned)((p->ldd / 8 + 255) / 256);
+    const unsigned gx = (unsigned)((nproc / 8 + 255) / 256);
     const dim3 rgrid(gx, (unsigned)std::min(m, 64));
     switch (p->i8_nmod) {
 #define SCS_RES_CASE(K)                                                                                            \
   case K:                                                                                                          \
-    LAUNCH(c, k_residues<K>, rgrid, 256, 0, p->dA, p->ldd, p->n, m, p->dw, p->d_colscale, p->d_planes, p->ldx);    \
+    LAUNCH(c, k_residues<K>, rgrid, 256, 0, p->dA + p->alo, p->ldd, nproc, m, p->dw + p->alo, p->d_colscale,      \
+           p->d_planes + p->alo, p->ldx);                                                                        \
     break;
       SCS_RES_CASE(10)
       SCS_RES_CASE(11)
@@ -641,17 +697,17 @@ static int run_gram_i8(scs_problem* p, int* done) {
       if (cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg) != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
       p->i8_clusters = nc;
     }
-    const int ncl = (int)std::min<int64_t>(p->i8_clusters, p->i8plan.units);
+    const int ncl = (int)std::min<int64_t>(p->i8_clusters, pl.units);
     cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
     CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
-    cudaError_t le = cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, p->i8plan, (const int2*)p->d_i8tiles,
+    cudaError_t le = cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
                                         p->d_i8partial, p->d_i8progress);
     c->launches += 1;
     if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
   }
   {
     StageTimer t(c, ST_GRAMFIN);
-    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, p->i8plan, p->d_ecol, p->i8_b, p->d_G);
+    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, p->d_ecol, p->i8_b, p->d_G);
   }
   *done = 1;
   return SCS_OK;
@@ -667,7 +723,7 @@ static int run_gram(scs_problem* p, XRef x) {
     LAUNCH(c, k_quadform_hess, dim3((m + 255) / 256, m), 256, 0, p->dA, p->ldd, m, p->d_G);
     return SCS_OK;
   }
-  bool want_i8 = p->gram_mode == 2 || (p->gram_mode == 0 && p->m >= 512 && p->n >= 32768);
+  bool want_i8 = p->gram_mode == 2 || (p->gram_mode == 0 && p->m >= 512 && p->win_hi - p->win_lo >= 32768);
   if (want_i8 && !p->i8_failed) {
     int done = 0;
     int rc = run_gram_i8(p, &done);
@@ -681,8 +737,10 @@ static int run_gram(scs_problem* p, XRef x) {
   p->last_gram_path = 1;
   {
     StageTimer t(c, ST_GRAM);
-    const int grid = (int)std::min<int64_t>(c->num_sms, p->plan.units);
-    LAUNCH(c, k_gram, grid, kGThreads, kGSmemBytes, p->amap, p->dw, m, p->ldp, p->plan, p->d_partial);
+    GramPlan pl = p->plan;
+    pl.kt = (p->ahi - p->alo) / kGBK;  // k-tiles of the active row window (the K split was planned for the whole shard)
+    const int grid = (int)std::min<int64_t>(c->num_sms, pl.units);
+    LAUNCH(c, k_gram, grid, kGThreads, kGSmemBytes, p->amap, p->dw, m, p->ldp, pl, p->alo / kGBK, p->d_partial);
   }
   {
     StageTimer t(c, ST_GRAMFIN);
@@ -904,10 +962,16 @@ static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind
   for (auto v : vecs) SCS_TRY(dalloc(v, p->mp));
   SCS_TRY(dalloc(&p->d_scal, SC_COUNT));
   CU_TRY(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 8) * sizeof(double)));
-  p->fwd_blocks = (n_local + kFwdRows - 1) / kFwdRows;
+  p->fwd_blocks = (p->ldd + kFwdRows - 1) / kFwdRows;
+  p->win_lo = 0;
+  p->win_hi = n_local;
+  p->alo = 0;
+  p->ahi = p->ldd;
+  p->win_rows_global = 0;  // resolved (all-reduced) by the first set_window
   p->adj_blocks = (p->ldd + 64 * 8 - 1) / (64 * 8);
   SCS_TRY(dalloc(&p->d_losspart, p->fwd_blocks));
   SCS_TRY(dalloc(&p->d_adjpart, (size_t)p->adj_blocks * m));
+  SCS_TRY(set_window(p, 0, n_local));  // whole shard; with several ranks this all-reduces the global row count
   return SCS_OK;
 }
 
@@ -976,8 +1040,8 @@ extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64
   // z = A x_true (a forward pass with the z-only loss kind), then labels / targets
   LossParams lp = p->loss;
   lp.kind = 2;
-  LAUNCH(ctx, k_forward<8>, (unsigned)p->fwd_blocks, kFwdThreads, 0, p->dA, p->ldd, p->n, (int)m, p->d_t1, p->dy, lp,
-         p->dz, (double*)nullptr, (double*)nullptr, p->d_losspart);
+  LAUNCH(ctx, k_forward<8>, (unsigned)p->fwd_blocks, kFwdThreads, 0, p->dA, p->ldd, p->ldd, (int64_t)0, p->n, (int)m,
+         p->d_t1, p->dy, lp, p->dz, (double*)nullptr, (double*)nullptr, p->d_losspart);
   LAUNCH(ctx, k_synth_y, (unsigned)((n_local + 255) / 256), 256, 0, p->dy, p->dz, n_local, row0, seed + 2,
          loss_kind == SCS_LOSS_LOGISTIC ? 0 : 1, 0.1);
   CU_TRY(cudaMemsetAsync(p->dz, 0, p->ldd * sizeof(double), ctx->stream));
@@ -1157,6 +1221,41 @@ extern "C" int scs_set_gram_mode(scs_problem* p, int mode) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   if (mode < 0 || mode > 2) return fail(SCS_INVALID_ARG, "gram mode must be 0 (auto), 1 (DMMA) or 2 (tcgen05 int8)");
   p->gram_mode = mode;
+  return SCS_OK;
+}
+extern "C" int scs_set_active_rows(scs_problem* p, int64_t row_lo, int64_t row_hi) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  return set_window(p, row_lo, row_hi);
+}
+extern "C" int scs_set_batches(scs_problem* p, int64_t nbatch, const int64_t* offsets) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (nbatch < 0 || (nbatch > 0 && !offsets)) return fail(SCS_INVALID_ARG, "bad batch table");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  p->batch_off.clear();
+  p->batch_rows_global.clear();
+  if (nbatch == 0) return set_window(p, 0, p->n);
+  if (offsets[0] != 0 || offsets[nbatch] > p->n) return fail(SCS_INVALID_ARG, "batch offsets must start at 0 and stay inside the shard");
+  for (int64_t i = 0; i < nbatch; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(SCS_INVALID_ARG, "batch offsets must be non-decreasing");
+  p->batch_off.assign(offsets, offsets + nbatch + 1);
+  // global batch sizes (and the global row count) in one all-reduce
+  std::vector<double> cnt(nbatch + 1);
+  for (int64_t i = 0; i < nbatch; ++i) cnt[i] = (double)(offsets[i + 1] - offsets[i]);
+  cnt[nbatch] = (double)p->n;
+  if (p->ctx->world > 1) {
+    double* d = nullptr;
+    CU_TRY(cudaMalloc((void**)&d, cnt.size() * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(d, cnt.data(), cnt.size() * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    int rc = allreduce(p->ctx, d, cnt.size());
+    if (rc == SCS_OK) {
+      cudaMemcpyAsync(cnt.data(), d, cnt.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream);
+      cudaStreamSynchronize(p->ctx->stream);
+    }
+    cudaFree(d);
+    SCS_TRY(rc);
+  }
+  for (double v : cnt) p->batch_rows_global.push_back((int64_t)(v + 0.5));
   return SCS_OK;
 }
 extern "C" int scs_set_stream_mode(scs_problem* p, int mode) {
@@ -1340,7 +1439,7 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
   if (p->method == SCS_METHOD_N || p->method == SCS_METHOD_GGN) {
     const bool ggn = p->method == SCS_METHOD_GGN;
     const int wk = ggn ? SCS_WEIGHTS_GGN : SCS_WEIGHTS_NEWTON;
-    if (ggn && (int64_t)p->n * c->world + 1 <= p->m && c->world == 1)
+    if (ggn && p->win_rows_global + 1 <= p->m)
       return fail(SCS_UNSUPPORTED,
                   "ProxGGNSCORE underdetermined branch (n+1 <= m, prox-GGN-SCORE.jl:124-127) is not implemented on the GPU");
     if (!type1 && p->ss_type != 2 && p->ss_type != 3) return fail(SCS_INVALID_ARG, "Please, choose ss_type in [1, 2, 3].");
@@ -1525,45 +1624,67 @@ extern "C" int scs_solve(scs_problem* p, const double* x0, const double* x_star,
   CU_TRY(cudaMemcpyAsync(p->vx[prv], x0, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   uint64_t id_cur = p->next_id++, id_prv = id_cur;
   SCS_TRY(scs_method_init(p));
+  // mini-batches (iterate.jl:139-145,204): the objective always sees the whole shard, step! one batch at a time
+  const bool batched = !p->batch_off.empty();
+  const int64_t iend = batched ? (int64_t)p->batch_off.size() - 1 : 1;
   double pri = nan, f_rel_error = 0;
   for (int64_t epoch_t = 1; epoch_t <= max_epoch; ++epoch_t) {
-    XRef xc{p->vx[cur], id_cur}, xp{p->vx[prv], id_prv};
     double f, r, e2, nx2;
-    SCS_TRY(objective_at(xc, &f, &r, &e2, &nx2));
+    if (batched) SCS_TRY(set_window(p, 0, p->n, p->batch_rows_global.back()));
+    {
+      XRef xc{p->vx[cur], id_cur};
+      SCS_TRY(objective_at(xc, &f, &r, &e2, &nx2));
+    }
     double o = f + r;
     f_rel_error = frel(o);
     push(o, f, pri, rel_err(e2), f_rel_error);
-    if (epoch_t == max_epoch) push(o, f, pri, rel_err(e2), f_rel_error);  // iterate.jl:219-231 (same values again)
-    const uint64_t id_new = p->next_id++;
-    SCS_TRY(step_device(p, xc, xp, epoch_t, p->vx[nxt], id_new, p->d_xstar));
-    CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SCS_TRY(ctx_sync(c));
-    pri = std::sqrt(p->h_scal[SC_PRI2]);
-    const double diff = std::sqrt(p->h_scal[SC_DIFF2]);
-    const double nx = std::sqrt(nx2);
-    const bool stop = diff < x_tol * std::max(nx, 1.0) || f_rel_error <= f_tol || pri < x_tol;  // :234
-    XRef xn{p->vx[nxt], id_new};
-    if (stop) {
-      if (epoch_t != max_epoch) {  // :235-247
+    double diff = 0, nx = 0;
+    for (int64_t i = 1; i <= iend; ++i) {
+      XRef xc{p->vx[cur], id_cur}, xp{p->vx[prv], id_prv};
+      if (epoch_t == max_epoch && i == iend) {  // iterate.jl:219-231: the current x once more
+        if (batched && i > 1) {
+          SCS_TRY(set_window(p, 0, p->n, p->batch_rows_global.back()));
+          SCS_TRY(objective_at(xc, &f, &r, &e2, &nx2));
+          o = f + r;
+        }
+        f_rel_error = frel(o);
+        push(o, f, pri, rel_err(e2), f_rel_error);
+      }
+      if (batched) SCS_TRY(set_window(p, p->batch_off[i - 1], p->batch_off[i], p->batch_rows_global[i - 1]));
+      const uint64_t id_new = p->next_id++;
+      SCS_TRY(step_device(p, xc, xp, epoch_t, p->vx[nxt], id_new, p->d_xstar));
+      CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SCS_TRY(ctx_sync(c));
+      pri = std::sqrt(p->h_scal[SC_PRI2]);
+      diff = std::sqrt(p->h_scal[SC_DIFF2]);
+      nx = std::sqrt(p->h_scal[SC_NX2]);  // ‖x‖ of the step's input (k_pre)
+      const bool stop = diff < x_tol * std::max(nx, 1.0) || f_rel_error <= f_tol || pri < x_tol;  // :234
+      XRef xn{p->vx[nxt], id_new};
+      if (stop && epoch_t != max_epoch) {  // :235-247
         double f2, r2, e22, n22;
+        if (batched) SCS_TRY(set_window(p, 0, p->n, p->batch_rows_global.back()));
         SCS_TRY(objective_at(xn, &f2, &r2, &e22, &n22));
         const double o2 = f2 + r2;
         f_rel_error = frel(o2);
         push(o2, f2, pri, rel_err(e22), f_rel_error);
       }
-      epochs += 1;
+      // x_prev = x; x = x_new
+      const int old_prv = prv;
+      prv = cur;
+      id_prv = id_cur;
+      cur = nxt;
+      id_cur = id_new;
+      nxt = old_prv;
+      if (stop) {
+        epochs += 1;
+        break;
+      }
     }
-    // x_prev = x; x = x_new
-    const int old_prv = prv;
-    prv = cur;
-    id_prv = id_cur;
-    cur = nxt;
-    id_cur = id_new;
-    nxt = old_prv;
-    // :257 — ‖x − x_prev‖ is the same ‖x⁺ − x‖ computed above
+    // :257 — ‖x − x_prev‖ is the ‖x⁺ − x‖ of the last step taken
     if (diff < x_tol * std::max(nx, 1.0) || f_rel_error <= f_tol || pri < x_tol) break;
     epochs += 1;
   }
+  if (batched) SCS_TRY(set_window(p, 0, p->n, p->batch_rows_global.back()));
   CU_TRY(cudaMemcpyAsync(x_out, p->vx[cur], m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SCS_TRY(ctx_sync(c));
   *n_hist = nh;

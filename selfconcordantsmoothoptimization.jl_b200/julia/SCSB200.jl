@@ -16,7 +16,7 @@ using SelfConcordantSmoothOptimization
 import SelfConcordantSmoothOptimization: iterate!, ProximalMethod, ProxNSCORE, ProxGGNSCORE, ProxLQNSCORE,
     Problem, Solution, PHuberSmootherL1L2, PHuberSmootherIndBox, PHuberSmootherGL, ExponentialSmootherIndBox,
     LogExpSmootherIndBox, OsBaSmootherL1L2, OsBaSmootherGL, bounds_sanity_check
-using LinearAlgebra, Dates
+using LinearAlgebra, Dates, Random
 
 export LogisticLoss, LeastSquaresLoss, QuadFormLoss, GPUContext, gpu_iterate!
 
@@ -159,19 +159,46 @@ function gpu_step(p::GPUProblem, x::Vector{Float64}, x_prev::Vector{Float64}, it
     return return_dx ? (x_new, dx, pri[]) : (x_new, pri[])
 end
 
+# rows [lo, hi) (0-based, half-open) of the resident shard take part in the following passes: one mini-batch
+set_active_rows!(p::GPUProblem, lo::Integer, hi::Integer) =
+    check(ccall((:scs_set_active_rows, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), p.h, lo, hi))
+
+# The data loader of optim_loop! (iterate.jl:122-145, utils.jl:14-25): row order after the one-time shuffle and the
+# batch offsets.  MLUtils.DataLoader(batchsize, shuffle, partial=true) gives ceil(n/b) consecutive batches.
+function batch_plan(n::Integer; batch_size=nothing, slice_samples=false, shuffle_batch=true, local_max_iter=nothing)
+    batch_size !== nothing && slice_samples && (slice_samples = false)
+    slice_samples && ((batch_size, shuffle_batch) = (1, false))
+    batch_size === nothing && ((batch_size, shuffle_batch) = (n, false))
+    order = shuffle_batch ? Random.shuffle(1:n) : nothing
+    max_iter = cld(n, batch_size)
+    iend = (local_max_iter !== nothing && Int(floor(local_max_iter)) > 0) ? min(Int(floor(local_max_iter)), max_iter) : max_iter
+    offsets = [min(i * batch_size, n) for i in 0:iend]
+    return order, offsets
+end
+
 # optim_loop! (iterate.jl:100-266) with the two hot call sites routed to the GPU; histories, stopping rules and the
-# Solution are the reference's.  Full batch only (mini-batch options are rejected, not emulated on the CPU).
+# Solution are the reference's.  Mini-batches: the rows are uploaded once in the loader's (shuffled) order, so every
+# batch is a contiguous row range of the resident matrix; the objective is always taken over all rows (:189).
 function gpu_iterate!(method::ProximalMethod, model, reg_name, hμ; ctx::GPUContext=GPUContext(0), α=nothing,
-                      batch_size=nothing, slice_samples=false, max_epoch=1000, x_tol=1e-10, f_tol=1e-10,
-                      smoother_bounds=nothing, kwargs...)
-    (batch_size !== nothing || slice_samples) && Base.error("scs_b200: mini-batch / slice_samples are not supported on the GPU path")
+                      batch_size=nothing, slice_samples=false, shuffle_batch=true, local_max_iter=nothing,
+                      max_epoch=1000, x_tol=1e-10, f_tol=1e-10, smoother_bounds=nothing, kwargs...)
     SelfConcordantSmoothOptimization.set_name!(method, [])
     α !== nothing && (model.L = 1 / α)
+    n = size(model.A, 1)
+    batched = batch_size !== nothing || slice_samples
+    order, offsets = batch_plan(n; batch_size=batch_size, slice_samples=slice_samples, shuffle_batch=shuffle_batch,
+                                local_max_iter=local_max_iter)
+    if order !== nothing   # one-time shuffle: upload the rows in loader order
+        model = deepcopy(model); model.A = model.A[order, :]; model.y = model.y[order]
+    end
+    windows = batched ? [(offsets[i], offsets[i+1]) for i in 1:length(offsets)-1] : [(0, n)]
+    iend = length(windows)
     p = GPUProblem(ctx, model)
     configure!(p, method, model, reg_name, hμ; smoother_bounds=smoother_bounds)
+    objective(v) = (batched && set_active_rows!(p, 0, n); gpu_objective(p, v))
     objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
     x_star = model.x
-    fs, rs = gpu_objective(p, x_star)
+    fs, rs = objective(x_star)
     obj_star = fs + rs
     x = copy(model.x0); x_prev = deepcopy(x)
     check(ccall((:scs_method_init, LIB), Cint, (Ptr{Cvoid},), p.h))
@@ -182,21 +209,24 @@ function gpu_iterate!(method::ProximalMethod, model, reg_name, hμ; ctx::GPUCont
     push_stat!(o, f, r, fr) = (push!(objs, o); push!(fvals, f); push!(pris, pri); push!(rels, r); push!(frels, fr);
                                push!(times, (now() - t0).value / 1000))
     for epoch_t in 1:max_epoch
-        f, r = gpu_objective(p, x); obj = f + r
+        f, r = objective(x); obj = f + r
         f_rel_error = frel(obj)
         push_stat!(obj, f, rel_err(x), f_rel_error)
-        if epoch_t == max_epoch
-            f, r = gpu_objective(p, x); obj = f + r; f_rel_error = frel(obj)
-            push_stat!(obj, f, rel_err(x), f_rel_error)
-        end
-        x_new, pri = gpu_step(p, x, x_prev, epoch_t)
-        if norm(x_new - x) < x_tol * max(norm(x), 1) || f_rel_error ≤ f_tol || pri < x_tol
-            if epoch_t != max_epoch
-                f, r = gpu_objective(p, x_new); obj = f + r; f_rel_error = frel(obj)
-                push_stat!(obj, f, rel_err(x_new), f_rel_error)
+        for (i, (lo, hi)) in enumerate(windows)
+            if epoch_t == max_epoch && i == iend
+                f, r = objective(x); obj = f + r; f_rel_error = frel(obj)
+                push_stat!(obj, f, rel_err(x), f_rel_error)
             end
-            x_prev = deepcopy(x); x = x_new; epochs += 1
-        else
+            batched && set_active_rows!(p, lo, hi)
+            x_new, pri = gpu_step(p, x, x_prev, epoch_t)
+            if norm(x_new - x) < x_tol * max(norm(x), 1) || f_rel_error ≤ f_tol || pri < x_tol
+                if epoch_t != max_epoch
+                    f, r = objective(x_new); obj = f + r; f_rel_error = frel(obj)
+                    push_stat!(obj, f, rel_err(x_new), f_rel_error)
+                end
+                x_prev = deepcopy(x); x = x_new; epochs += 1
+                break
+            end
             x_prev = deepcopy(x); x = x_new
         end
         if norm(x - x_prev) < x_tol * max(norm(x_prev), 1) || f_rel_error ≤ f_tol || pri < x_tol

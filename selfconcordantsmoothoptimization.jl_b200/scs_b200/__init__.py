@@ -5,6 +5,7 @@ Python host mirror of the reference interface over the C ABI in include/scs_b200
 """
 from ._capi import LIB_PATH, EXPORTS, ScsError, UnsupportedError  # noqa: F401
 from .api import (Context, default_context, Problem, ProblemGeneric, get_P, Solution, iterate,  # noqa: F401
+                  batch_plan, batch_shard,
                   LogisticLoss, LeastSquaresLoss, QuadFormLoss,
                   PHuberSmootherL1L2, PHuberSmootherIndBox, PHuberSmootherGL, ExponentialSmootherIndBox,
                   LogExpSmootherIndBox, OsBaSmootherL1L2, OsBaSmootherGL,

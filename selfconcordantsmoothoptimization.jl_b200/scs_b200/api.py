@@ -178,6 +178,7 @@ class Problem:
         self.x = np.zeros_like(self.x0) if sol is None else K.vec(sol, self.x0.shape[0])  # problems.jl:70
         self._h = C.c_void_p()
         self._reg_name = None
+        self._host = None  # (A, y) as given: needed again only if iterate!(shuffle_batch=true) reorders the rows
         if A is not None:
             A = np.asarray(A, dtype=np.float64)
             if A.ndim != 2:
@@ -188,8 +189,40 @@ class Problem:
             if A.shape[1] != self.x0.shape[0]:
                 raise ValueError("x0 length must equal the number of columns of A")
             self.n, self.m = A.shape
+            self._host = (A, yv)
             K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A), self.n, self.m, A.shape[0], K.dptr(yv),
                                                f.kind, f.param(), f.label_code(), C.byref(self._h)))
+
+    def reorder_rows(self, order):
+        """Lay the shard out in the given row order (the data loader's one-time shuffle, utils.jl:18-25): the device
+        copy is rebuilt from the host arrays, so every mini-batch becomes a contiguous row range."""
+        if self._host is None:
+            raise UnsupportedError(K.SCS_UNSUPPORTED, "a shard generated on the device cannot be shuffled; build the "
+                                                      "problem from host arrays or pass shuffle_batch=False")
+        A, yv = self._host
+        order = np.asarray(order, dtype=np.int64)
+        A2 = np.asfortranarray(A[order])
+        y2 = np.ascontiguousarray(yv[order])
+        K.lib().scs_problem_destroy(self._h)
+        self._h = C.c_void_p()
+        self._host = (A2, y2)
+        self._reg_name = None
+        K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A2), self.n, self.m, A2.shape[0], K.dptr(y2),
+                                           self.f.kind, self.f.param(), self.f.label_code(), C.byref(self._h)))
+        for name, val in getattr(self, "_modes", {}).items():  # kernel selections survive the rebuild
+            getattr(self, name)(val)
+
+    def set_active_rows(self, lo, hi):
+        """Rows [lo, hi) of the shard take part in the following passes (one mini-batch); (0, n) = all."""
+        K.check(K.lib().scs_set_active_rows(self._h, int(lo), int(hi)))
+
+    def set_batches(self, offsets):
+        """Batch table for the in-library loop (scs_solve): local offsets, len = nbatch + 1; None = full batch."""
+        if offsets is None:
+            K.check(K.lib().scs_set_batches(self._h, 0, None))
+            return
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        K.check(K.lib().scs_set_batches(self._h, len(off) - 1, K.iptr(off)))
 
     @classmethod
     def synthetic(cls, n_total, m, f, lam, *, x0=None, row0=0, n_local=None, seed=1234, density=1.0, ctx=None, **kw):
@@ -305,6 +338,7 @@ class Problem:
     def set_gram_mode(self, mode):
         """"auto" | "dmma" | "i8": which Gram kernel builds A'diag(w)A (the int8 tcgen05 path needs w >= 0)."""
         K.check(K.lib().scs_set_gram_mode(self._h, {"auto": 0, "dmma": 1, "i8": 2}[mode]))
+        self.__dict__.setdefault("_modes", {})["set_gram_mode"] = mode
 
     def gram_path(self):
         v = C.c_int()
@@ -314,6 +348,7 @@ class Problem:
     def set_gram_bits(self, bits):
         """Fixed-point bits kept below each column's largest entry by the emulated-fp64 Gram (24..50, default 40)."""
         K.check(K.lib().scs_set_gram_bits(self._h, int(bits)))
+        self.__dict__.setdefault("_modes", {})["set_gram_bits"] = bits
 
     def gram_info(self):
         """(moduli used, bits kept) by the emulated-fp64 Gram; (0, 0) before it has run."""
@@ -324,6 +359,7 @@ class Problem:
     def set_stream_mode(self, mode):
         """"auto" | "two_pass" | "fused": how objective + gradient at the same x read A (once or twice)."""
         K.check(K.lib().scs_set_stream_mode(self._h, {"auto": 0, "two_pass": 1, "fused": 2}[mode]))
+        self.__dict__.setdefault("_modes", {})["set_stream_mode"] = mode
 
     def stream_path(self):
         v = C.c_int()
@@ -476,20 +512,59 @@ def _norm(v):
     return float(np.linalg.norm(v))
 
 
+def batch_plan(n, batch_size=None, slice_samples=False, shuffle_batch=False, local_max_iter=None, perm=None):
+    """(row order, batch offsets) of optim_loop!'s data loader (iterate.jl:122-145, utils.jl:14-25) for n rows.
+
+    MLUtils.DataLoader(batchsize, shuffle, partial=true): ceil(n/b) consecutive batches of the once-shuffled order,
+    collected ONCE before the epoch loop; slice_samples = one row per step (batch_size wins if both are given);
+    local_max_iter keeps the first min(floor(local_max_iter), max_iter) batches.  order is None when the rows stay
+    where they are.  The shuffle itself is Julia's RNG upstream: here the permutation is an input (perm), or a
+    fixed-seed numpy permutation when omitted."""
+    if batch_size is not None and slice_samples:
+        slice_samples = False  # iterate.jl:127-130
+    if slice_samples:
+        batch_size, shuffle_batch = 1, False
+    if batch_size is None:
+        batch_size, shuffle_batch = n, False
+    batch_size = int(batch_size)
+    if batch_size < 1:
+        raise ScsError(K.SCS_INVALID_ARG, "batch_size must be positive")
+    order = None
+    if shuffle_batch:
+        order = np.random.default_rng(1234).permutation(n) if perm is None else np.asarray(perm, dtype=np.int64)
+        if order.shape != (n,) or not np.array_equal(np.sort(order), np.arange(n)):
+            raise ScsError(K.SCS_INVALID_ARG, "perm must be a permutation of 0..n-1")
+    max_iter = -(-n // batch_size)
+    iend = max_iter
+    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
+        iend = min(int(np.floor(local_max_iter)), max_iter)
+    offsets = np.minimum(np.arange(iend + 1, dtype=np.int64) * batch_size, n)
+    return order, offsets
+
+
 def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_size=None, slice_samples=False,
             shuffle_batch=True, max_epoch=1000, comm_rounds=100, local_max_iter=None, x_tol=1e-10, f_tol=1e-10,
-            verbose=1, device_loop=False):
-    """iterate!(method, model, reg_name, hμ; ...) — iterate.jl:56-76 → optim_loop! :100-266 (full batch).
+            verbose=1, device_loop=False, perm=None, batch_offsets=None):
+    """iterate!(method, model, reg_name, hμ; ...) — iterate.jl:56-76 → optim_loop! :100-266.
 
-    device_loop=False: the epoch loop runs here and calls scs_objective / scs_step once per epoch (what the Julia
-    shim does).  device_loop=True: the same loop runs inside the library (scs_solve), x never leaves HBM.
+    device_loop=False: the epoch loop runs here and calls scs_objective / scs_step (what the Julia shim does).
+    device_loop=True: the same loop runs inside the library (scs_solve), x never leaves HBM.
+    Mini-batches: the objective is taken over all rows every epoch, step! over one batch at a time (:204-233).  On one
+    rank the batches are laid out here (rows are re-uploaded once in shuffled order when shuffle_batch is set); with
+    several ranks the caller shards every batch over the ranks and passes this rank's local offsets (batch_offsets).
     """
     import time
-    if batch_size is not None or slice_samples or local_max_iter is not None:
-        raise UnsupportedError(K.SCS_UNSUPPORTED, "mini-batch / slice_samples / local_max_iter are not supported on "
-                                                  "the GPU path yet (full batch only)")
     if metrics is not None:
         raise UnsupportedError(K.SCS_UNSUPPORTED, "user metric callbacks would have to read A on the host")
+    offsets = None
+    if batch_offsets is not None:
+        offsets = np.asarray(batch_offsets, dtype=np.int64)
+    elif batch_size is not None or slice_samples:
+        if model.ctx.world > 1:
+            raise UnsupportedError(K.SCS_UNSUPPORTED, "with several ranks pass batch_offsets (see batch_shard)")
+        order, offsets = batch_plan(model.n, batch_size, slice_samples, shuffle_batch, local_max_iter, perm)
+        if order is not None:
+            model.reorder_rows(order)
     method.set_name()  # iterate.jl:112
     if alpha is not None:
         model.L = 1 / alpha  # :113-115
@@ -501,8 +576,12 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
         xo = np.empty(m)
         h = [np.empty(cap) for _ in range(5)]
         nh, ep = C.c_int64(), C.c_int64()
-        K.check(K.lib().scs_solve(model._h, K.dptr(model.x0), K.dptr(x_star), int(max_epoch), float(x_tol),
-                                  float(f_tol), K.dptr(xo), *[K.dptr(a) for a in h], C.byref(nh), C.byref(ep)))
+        model.set_batches(offsets)
+        try:
+            K.check(K.lib().scs_solve(model._h, K.dptr(model.x0), K.dptr(x_star), int(max_epoch), float(x_tol),
+                                      float(f_tol), K.dptr(xo), *[K.dptr(a) for a in h], C.byref(nh), C.byref(ep)))
+        finally:
+            model.set_batches(None)
         k = nh.value
         pri = [None if np.isnan(v) else float(v) for v in h[2][:k]]
         return Solution(xo, list(h[0][:k]), list(h[1][:k]), pri, [], list(h[3][:k]), list(h[4][:k]), {}, [], ep.value,
@@ -511,7 +590,16 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
     objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
     epochs = 0
     pri_res_norm = None
-    fs, rs = model.objective(x_star)
+    batched = offsets is not None
+    windows = [(int(offsets[i]), int(offsets[i + 1])) for i in range(len(offsets) - 1)] if batched else [(0, model.n)]
+    iend = len(windows)
+
+    def objective(v):  # always over the whole data (iterate.jl:168,189)
+        if batched:
+            model.set_active_rows(0, model.n)
+        return model.objective(v)
+
+    fs, rs = objective(x_star)
     with np.errstate(all="ignore"):
         obj_star = fs + rs  # :179
     x = model.x0.copy()
@@ -532,29 +620,55 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
         objs.append(o), fvals.append(f), pris.append(p), rels.append(r), frels.append(fr)
         times.append(time.perf_counter() - t0)
 
-    for epoch_t in range(1, int(max_epoch) + 1):
-        fval, reg = model.objective(x)
-        obj = fval + reg
-        rel_error = rel_err(x)
-        f_rel_error = frel(obj)
-        push(obj, fval, pri_res_norm, rel_error, f_rel_error)
-        if epoch_t == max_epoch:  # :219-231
-            fval, reg = model.objective(x)
+    try:
+        for epoch_t in range(1, int(max_epoch) + 1):
+            fval, reg = objective(x)
             obj = fval + reg
+            rel_error = rel_err(x)
             f_rel_error = frel(obj)
-            push(obj, fval, pri_res_norm, rel_err(x), f_rel_error)
-        x_new, pri_res_norm = model.step(x, x_prev, epoch_t)  # :233
-        if _norm(x_new - x) < x_tol * max(_norm(x), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :234
-            if epoch_t != max_epoch:
-                fval, reg = model.objective(x_new)
-                obj = fval + reg
-                f_rel_error = frel(obj)
-                push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error)
-            x_prev, x = x.copy(), x_new
+            push(obj, fval, pri_res_norm, rel_error, f_rel_error)
+            for i, (lo, hi) in enumerate(windows, start=1):  # :204
+                if epoch_t == max_epoch and i == iend:  # :219-231
+                    fval, reg = objective(x)
+                    obj = fval + reg
+                    f_rel_error = frel(obj)
+                    push(obj, fval, pri_res_norm, rel_err(x), f_rel_error)
+                if batched:
+                    model.set_active_rows(lo, hi)
+                x_new, pri_res_norm = model.step(x, x_prev, epoch_t)  # :233
+                if _norm(x_new - x) < x_tol * max(_norm(x), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :234
+                    if epoch_t != max_epoch:
+                        fval, reg = objective(x_new)
+                        obj = fval + reg
+                        f_rel_error = frel(obj)
+                        push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error)
+                    x_prev, x = x.copy(), x_new
+                    epochs += 1
+                    break
+                x_prev, x = x.copy(), x_new
+            if _norm(x - x_prev) < x_tol * max(_norm(x_prev), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :257
+                break
             epochs += 1
-        else:
-            x_prev, x = x.copy(), x_new
-        if _norm(x - x_prev) < x_tol * max(_norm(x_prev), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :257
-            break
-        epochs += 1
+    finally:
+        if batched:
+            model.set_active_rows(0, model.n)
     return Solution(x, objs, fvals, pris, [], rels, frels, {}, times, epochs, model)
+
+
+def batch_shard(n, world, rank, batch_size, local_max_iter=None, perm=None):
+    """Row ids (global, in upload order) and local batch offsets of one rank when every mini-batch of the global
+    problem is split evenly over the ranks: rank r holds rows shard_rows(len(batch), world, r) of each batch, batch
+    after batch, followed by its share of the rows no batch uses (local_max_iter), so that the objective still sees
+    every row."""
+    from .dist import shard_rows
+    order, offsets = batch_plan(n, batch_size, False, perm is not None, local_max_iter, perm)
+    order = np.arange(n) if order is None else order
+    rows, loc = [], [0]
+    bounds = list(offsets) + ([n] if offsets[-1] < n else [])
+    for i in range(len(bounds) - 1):
+        b0, b1 = int(bounds[i]), int(bounds[i + 1])
+        r0, cnt = shard_rows(b1 - b0, world, rank)
+        rows.append(order[b0 + r0:b0 + r0 + cnt])
+        if i < len(offsets) - 1:
+            loc.append(loc[-1] + cnt)
+    return np.concatenate(rows), np.asarray(loc, dtype=np.int64)

@@ -163,8 +163,10 @@ def test_error_behaviour(scs):
     with pytest.raises(scs.ScsError, match="bounds"):  # prox-reg-utils.jl:154
         p.C_set = (-1.0, 1.0)
         scs.iterate(scs.ProxNSCORE(), p, "indbox", scs.PHuberSmootherIndBox(np.zeros(3), np.ones(3), 1.0), verbose=0)
-    with pytest.raises(scs.UnsupportedError):  # mini-batching: not on the GPU path yet
-        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), batch_size=10, verbose=0)
+    with pytest.raises(scs.UnsupportedError):  # metric callbacks would need A on the host
+        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), metrics={"acc": lambda m, x: 0.0}, verbose=0)
+    with pytest.raises(scs.ScsError):  # a mini-batch window must stay inside the shard
+        p.set_active_rows(0, A.shape[0] + 1)
     with pytest.raises(scs.UnsupportedError):  # GGN underdetermined branch
         pw = scs.Problem(A[:10], y[:10], x0, scs.LogisticLoss(1 / 50), 0.1)
         scs.iterate(scs.ProxGGNSCORE(), pw, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0)
