@@ -322,6 +322,90 @@ __global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ M, 
   if (blockIdx.x == 0 && tid < nb) d[k0 + tid] = dk[tid];
 }
 
+// ---- ProxGGNSCORE underdetermined branch (n+1 <= m, prox-GGN-SCORE.jl:124-127) ----------------------------------
+// With N = n+1, Q = diag(q, 0), Jt = [J' | λ gr], J = diag(s) A the reference solves (I + Q Jt' H⁻¹ Jt) B = [res; 1]
+// and returns d = H⁻¹ Jt B.  The last row of Q is zero, so B_N = 1 and the first n unknowns satisfy
+//     (I + diag(q s) T diag(s)) B' = res − λ (q s) ∘ u,   T = A H⁻¹ A' (n x n),  u = A H⁻¹ gr,
+// after which d = H⁻¹ (A' (s ∘ B') + λ gr).  T is a Gram over the COLUMNS of A (K = m), the transpose of the tall
+// branch's; n < m <= 8192 here, so a plain tiled fp64 kernel is enough.
+// T[i,k] = sum_j A[i,j] A[k,j] hinv[j] for the lower 64x64 tiles (i >= k), mirrored.  A: rows [0,n) of the window.
+__global__ void __launch_bounds__(256)
+k_rowgram(const double* __restrict__ A, int64_t ldd, int n, int m, const double* __restrict__ hr, double* __restrict__ T,
+          int ldt) {
+  __shared__ double Ai[16][65], Ak[16][65];
+  int ti, tk;
+  {
+    const int tt = blockIdx.x;
+    int r = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= tt) ++r;
+    while (r * (r + 1) / 2 > tt) --r;
+    ti = r;
+    tk = tt - r * (r + 1) / 2;
+  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  double acc[4][4] = {};
+  for (int j0 = 0; j0 < m; j0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int jj = e >> 6, rr = e & 63, j = j0 + jj;
+      const int ri = ti * 64 + rr, rk = tk * 64 + rr;
+      const double hinv = j < m ? 1.0 / hr[j] : 0.0;
+      Ai[jj][rr] = (j < m && ri < n) ? A[(int64_t)j * ldd + ri] * hinv : 0.0;
+      Ak[jj][rr] = (j < m && rk < n) ? A[(int64_t)j * ldd + rk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = Ai[jj][ty + 16 * u];
+        b[u] = Ak[jj][tx + 16 * u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = ti * 64 + ty + 16 * u, k = tk * 64 + tx + 16 * v;
+      if (i < n && k < n) {
+        T[(int64_t)k * ldt + i] = acc[u][v];
+        if (ti != tk) T[(int64_t)i * ldt + k] = acc[u][v];
+      }
+    }
+}
+// M = I + diag(q s) T diag(s) in place (column-major, ld = ldt);  rhs = res − λ (q s) ∘ u
+__global__ void k_wide_system(double* __restrict__ T, int ldt, int n, const double* __restrict__ s,
+                              const double* __restrict__ res, const double* __restrict__ q,
+                              const double* __restrict__ u, double lam, double* __restrict__ rhs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (i >= n) return;
+  const double c = q[i] * s[i];
+  T[(int64_t)k * ldt + i] = (i == k ? 1.0 : 0.0) + (c * T[(int64_t)k * ldt + i]) * s[k];
+  if (k == 0) rhs[i] = res[i] - lam * (c * u[i]);
+}
+// t = s ∘ B'
+__global__ void k_wide_scale(const double* __restrict__ s, const double* __restrict__ b, int n, double* __restrict__ t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = s[i] * b[i];
+}
+// d = (g + λ gr) / Hr
+__global__ void k_wide_dir(const double* __restrict__ g, const double* __restrict__ gr, const double* __restrict__ hr,
+                           double lam, int m, double* __restrict__ d) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) d[j] = (g[j] + lam * gr[j]) / hr[j];
+}
+// v = gr / Hr
+__global__ void k_wide_v(const double* __restrict__ gr, const double* __restrict__ hr, int m, double* __restrict__ v) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) v[j] = gr[j] / hr[j];
+}
+
 // ---- pivoted LU fallback (unblocked, right-looking) -------------------------------------------
 // Fill the upper triangle from the lower one.
 __global__ void k_symmetrize(double* __restrict__ M, int64_t ld, int m) {

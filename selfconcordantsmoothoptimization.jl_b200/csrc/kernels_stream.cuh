@@ -39,12 +39,18 @@ SCS_DEVINL void loss_row(const LossParams& lp, double z, double y, double& term,
       const double om = 1.0 - yhat;
       const double res = -lp.p * (yc / yhat - (1.0 - yc) / om);
       const double q = lp.p * (yc / (yhat * yhat) + (1.0 - yc) / (om * om));
-      r = s * res;
-      w = (s * s) * q;
+      if (lp.weight_kind == 2) {  // wide branch (prox-GGN-SCORE.jl:124-127) wants the pieces, not the products
+        r = res;
+        w = q;
+        term = s;  // NB: the caller of kind 2 reads the Jacobian scale from `term`
+      } else {
+        r = s * res;
+        w = (s * s) * q;
+      }
     }
   } else if (lp.kind == 1) {  // least squares: 0.5*sum((z-y)^2)/p
     const double d = z - y;
-    term = d * d;
+    term = lp.weight_kind == 2 ? 1.0 : d * d;  // kind 2: Jacobian scale (out_fn = A x)
     r = d / lp.p;
     w = 1.0 / lp.p;
   } else {  // quadform: the pass only produces z
@@ -112,6 +118,11 @@ k_forward(const double* __restrict__ A, int64_t ldd, int64_t nproc, int64_t row_
     if (i0 < row_lo || i0 >= row_hi) t0 = r0 = w0 = z0 = 0.0;
     if (i0 + 1 < row_lo || i0 + 1 >= row_hi) t1 = r1 = w1 = z1 = 0.0;
     part = t0 + t1;
+    if (lp.weight_kind == 2) {  // GGN parts: z_out carries the Jacobian scale s, r_out = residual, w_out = Q_ii
+      z0 = t0;
+      z1 = t1;
+      part = 0.0;
+    }
     if (z_out) *reinterpret_cast<double2*>(z_out + i0) = make_double2(z0, z1);
     if (r_out) *reinterpret_cast<double2*>(r_out + i0) = make_double2(r0, r1);
     if (w_out) *reinterpret_cast<double2*>(w_out + i0) = make_double2(w0, w1);

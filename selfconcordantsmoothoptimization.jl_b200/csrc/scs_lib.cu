@@ -210,6 +210,7 @@ struct scs_problem {
   int fu_cluster = 1, fu_clusters = 0;
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
+  double* d_u = nullptr;  // row vector of the GGN wide branch (ldd doubles, allocated on first use)
   // l-bfgs
   double *d_S = nullptr, *d_Y = nullptr;
   int64_t* d_state = nullptr;
@@ -813,6 +814,57 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   return SCS_OK;
 }
 
+// ProxGGNSCORE underdetermined branch (rows + 1 <= m, prox-GGN-SCORE.jl:124-127) on the rows of the active window;
+// leaves gr, Hr, the damping scalars (k_pre) and d (before negation) in d_gr, d_hr, d_scal, d_sol.  See kernels_solve.cuh.
+static int run_ggn_wide(scs_problem* p, XRef x, double lam) {
+  scs_ctx* c = p->ctx;
+  if (c->world > 1)
+    return fail(SCS_UNSUPPORTED, "ProxGGNSCORE underdetermined branch (n+1 <= m) needs all rows of the batch on one GPU");
+  const int m = (int)p->m;
+  const int nb = (int)(p->win_hi - p->win_lo);
+  if (nb < 1) return fail(SCS_INVALID_ARG, "empty batch");
+  SCS_TRY(gram_setup(p));
+  if (!p->d_u) SCS_TRY(dalloc(&p->d_u, p->ldd));
+  {
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, (const double*)nullptr, m, p->d_gr, p->d_hr, p->d_rhs, p->d_scal);
+    LAUNCH(c, k_wide_v, (m + 255) / 256, 256, 0, p->d_gr, p->d_hr, m, p->d_t1);
+  }
+  // pieces s, res, q of the (out_fn, f(y,ŷ)) pair for the window's rows -> dz, dr, dw
+  SCS_TRY(run_forward(p, x.d, 2));
+  p->fwd_id = 0;  // not a pass the caches know about (no loss sum, z replaced by s)
+  p->grad_id = 0;
+  p->loss_reduced = false;
+  {
+    StageTimer t(c, ST_FWD);  // u = A (gr ./ Hr)
+    LossParams lp = p->loss;
+    lp.kind = 2;
+    lp.weight_kind = 0;
+    const int64_t nproc = p->ahi - p->alo;
+    LAUNCH(c, k_forward<8>, (unsigned)((nproc + kFwdRows - 1) / kFwdRows), kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc,
+           p->win_lo - p->alo, p->win_hi - p->alo, m, (const double*)p->d_t1, p->dy + p->alo, lp, p->d_u + p->alo,
+           (double*)nullptr, (double*)nullptr, p->d_losspart);
+  }
+  StageTimer t(c, ST_SOLVE);
+  const int nt = (nb + 63) / 64;
+  LAUNCH(c, k_rowgram, nt * (nt + 1) / 2, 256, 0, p->dA + p->win_lo, p->ldd, nb, m, p->d_hr, p->d_G, nb);
+  LAUNCH(c, k_wide_system, dim3((nb + 255) / 256, nb), 256, 0, p->d_G, nb, nb, p->dz + p->win_lo, p->dr + p->win_lo,
+         p->dw + p->win_lo, p->d_u + p->win_lo, lam, p->d_q);
+  // general (non-symmetric) system: partial-pivoting LU on the device
+  CU_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), c->stream));
+  for (int k = 0; k < nb; ++k) {
+    LAUNCH(c, k_lu_pivot, 1, kVecThreads, 0, p->d_G, (int64_t)nb, nb, k, p->d_q, p->d_info);
+    const int rem = nb - k - 1;
+    if (rem > 0) LAUNCH(c, k_lu_update, dim3((rem + 255) / 256, (rem + 15) / 16), 256, 0, p->d_G, (int64_t)nb, nb, k, p->d_q);
+  }
+  LAUNCH(c, k_lu_backsolve, 1, kVecThreads, 0, p->d_G, (int64_t)nb, nb, p->d_q, p->d_t2);
+  LAUNCH(c, k_wide_scale, (nb + 255) / 256, 256, 0, p->dz + p->win_lo, p->d_t2, nb, p->d_u + p->win_lo);
+  SCS_TRY(run_adjoint(p, p->d_u, p->d_t1));
+  LAUNCH(c, k_wide_dir, (m + 255) / 256, 256, 0, p->d_t1, p->d_gr, p->d_hr, lam, m, p->d_sol);
+  p->last_used_fallback = 1;
+  return SCS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // exported: misc
 // ------------------------------------------------------------------------------------------------
@@ -985,7 +1037,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss};
+                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
@@ -1439,9 +1491,7 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
   if (p->method == SCS_METHOD_N || p->method == SCS_METHOD_GGN) {
     const bool ggn = p->method == SCS_METHOD_GGN;
     const int wk = ggn ? SCS_WEIGHTS_GGN : SCS_WEIGHTS_NEWTON;
-    if (ggn && p->win_rows_global + 1 <= p->m)
-      return fail(SCS_UNSUPPORTED,
-                  "ProxGGNSCORE underdetermined branch (n+1 <= m, prox-GGN-SCORE.jl:124-127) is not implemented on the GPU");
+    const bool wide = ggn && p->win_rows_global + 1 <= p->m;  // prox-GGN-SCORE.jl:124
     if (!type1 && p->ss_type != 2 && p->ss_type != 3) return fail(SCS_INVALID_ARG, "Please, choose ss_type in [1, 2, 3].");
     if (p->ss_type == 2) {
       // prox-N-SCORE.jl:81-83 / prox-GGN-SCORE.jl:78-80 reference an undefined ∇f: the reference throws after iter 1
@@ -1451,19 +1501,24 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
         return fail(SCS_UNSUPPORTED,
                     "ss_type=2 is broken in the reference for ProxNSCORE/ProxGGNSCORE (UndefVarError: ∇f); rejected");
     }
-    SCS_TRY(ensure_grad(p, x, wk));
-    SCS_TRY(run_gram(p, x));
-    {
-      StageTimer t(c, ST_VEC);
-      LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_rhs, p->d_scal);
-      LAUNCH(c, k_add_diag, (m + 255) / 256, 256, 0, p->d_G, m, lam, p->d_hr);
-      CU_TRY(cudaMemcpyAsync(p->d_q, p->d_rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (wide) {
+      SCS_TRY(run_ggn_wide(p, x, lam));
+    } else {
+      SCS_TRY(ensure_grad(p, x, wk));
+      SCS_TRY(run_gram(p, x));
+      {
+        StageTimer t(c, ST_VEC);
+        LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_rhs, p->d_scal);
+        LAUNCH(c, k_add_diag, (m + 255) / 256, 256, 0, p->d_G, m, lam, p->d_hr);
+        CU_TRY(cudaMemcpyAsync(p->d_q, p->d_rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      }
+      SCS_TRY(run_solve(c, p->d_G, p->d_Gsave, p->d_Linv, p->d_info, p->d_q, p->d_t1, p->d_sol, m,
+                        &p->last_used_fallback));
     }
-    SCS_TRY(run_solve(c, p->d_G, p->d_Gsave, p->d_Linv, p->d_info, p->d_q, p->d_t1, p->d_sol, m,
-                      &p->last_used_fallback));
     if (p->ss_type == 3) {
       const double* gqx = p->d_rhs;  // N: ∇q = grad_f + λgr
       if (ggn) {                     // GGN's rhs is J'res + λgr; the line search wants the gradient of f(A,y,x)
+        // (compute_gq's k_pre recomputes gr / Hr / η² at the same x into scratch: d_gr, d_hr, SC_ETASQ stay valid)
         SCS_TRY(compute_gq(p, x, lam, p->d_gnewton));
         gqx = p->d_gnewton;
       }

@@ -80,10 +80,16 @@ def test_slice_samples(scs):
         assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj)
         assert relerr(sg.x, so.x) <= 1e-9 or np.linalg.norm(so.x) < 1e-12
         assert hist_err(sg.obj, so.obj) <= 1e-9
-    # GGN on one row is the underdetermined branch (n+1 <= m): rejected, never run on the CPU
-    with pytest.raises(scs.UnsupportedError):
-        scs.iterate(scs.ProxGGNSCORE(), pg, "l1", scs.PHuberSmootherL1L2(1), slice_samples=True, max_epoch=2, verbose=0)
     pg.close()
+
+
+def test_small_batches_take_the_ggn_wide_branch(scs):
+    """Mini-batches of fewer rows than variables: every step! is the underdetermined GGN branch (n_batch+1 <= m)."""
+    so, sg, modelg, reg = run_pair(scs, "c2_logreg_ggn_l1", True, batch_size=200, local_max_iter=4)
+    assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj)
+    assert relerr(sg.x, so.x) <= 1e-9, relerr(sg.x, so.x)
+    assert hist_err(sg.obj, so.obj) <= 1e-9
+    modelg.close()
 
 
 def test_active_rows_components(scs):

@@ -167,9 +167,6 @@ def test_error_behaviour(scs):
         scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), metrics={"acc": lambda m, x: 0.0}, verbose=0)
     with pytest.raises(scs.ScsError):  # a mini-batch window must stay inside the shard
         p.set_active_rows(0, A.shape[0] + 1)
-    with pytest.raises(scs.UnsupportedError):  # GGN underdetermined branch
-        pw = scs.Problem(A[:10], y[:10], x0, scs.LogisticLoss(1 / 50), 0.1)
-        scs.iterate(scs.ProxGGNSCORE(), pw, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0)
     p.close()
 
 
@@ -188,3 +185,31 @@ def test_config_parity_i8_gram(scs, name):
     if reg in ("l1", "gl"):
         assert np.array_equal(sg.x != 0, so.x != 0)
     modelg.close()
+
+
+# ---- ProxGGNSCORE underdetermined branch: n + 1 <= m (prox-GGN-SCORE.jl:124-127) -------------------------------
+@pytest.mark.parametrize("n,m,loss", [(10, 50, "logistic"), (40, 100, "consistent"), (63, 64, "ls"), (1, 2, "logistic"),
+                                      (200, 777, "consistent"), (129, 300, "ls")])
+@pytest.mark.parametrize("ss_type", [1, 3])
+def test_ggn_wide_branch(scs, n, m, loss, ss_type):
+    from oracle import synth
+    A = synth.make_A(n, m, seed=11)
+    x0 = synth.make_x0(m, seed=12) * 0.3
+    if loss == "ls":
+        y = synth.make_targets_ls(A @ synth.make_x_true(m, seed=13), seed=14)
+        Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
+    else:
+        y = synth.make_labels_logistic(A @ synth.make_x_true(m, seed=13, frac=0.3), seed=14)
+        mode = "consistent" if loss == "consistent" else "literal"
+        Lo, Lg = O.LogisticLoss(1 / n, mode), scs.LogisticLoss(1 / n, mode)
+    so = O.iterate(O.ProxGGNSCORE(ss_type=ss_type), O.Problem(A, y, x0, Lo, 1e-2), "l1", O.PHuberSmootherL1L2(1.0),
+                   max_epoch=5, alpha=0.9)
+    for device_loop in (False, True):
+        pg = scs.Problem(A, y, x0, Lg, 1e-2)
+        sg = scs.iterate(scs.ProxGGNSCORE(ss_type=ss_type), pg, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=5, alpha=0.9,
+                         verbose=0, device_loop=device_loop)
+        assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj)
+        assert relerr(sg.x, so.x) <= 1e-9, relerr(sg.x, so.x)  # a general n x n LU sits in the middle of every step
+        assert hist_err(sg.obj, so.obj) <= 1e-9
+        assert np.array_equal(sg.x != 0, so.x != 0)
+        pg.close()
