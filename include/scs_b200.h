@@ -25,6 +25,7 @@
  *   scs_step                step!(method, model, reg_name, hμ, As, x, x_prev, ys, Cmat, iter; return_dx)
  *                                                                           iterate.jl:52-54,233; prox-*-SCORE.jl step!
  *   scs_solve               optim_loop!(method, model, reg_name, hμ; opt)   iterate.jl:100-266
+ *   scs_set_test_problem    model.Atest / model.ytest, ftest(x), Solution.fvaltest          iterate.jl:169-176, utils.jl:55-57
  *   scs_set_batches /       get_data_loader / get_loader_subset / the inner `for (i, sample) in enumerate(data)`
  *   scs_set_active_rows                                                     iterate.jl:139-145,204-207, utils.jl:14-25
  *   scs_loss_eval           f / gradient(f,x) / out_fn pieces               prox-N-SCORE.jl:49-69, prox-GGN-SCORE.jl:44-56
@@ -130,6 +131,12 @@ int scs_get_gram_info(scs_problem* p, int* nmod, int* bits);
  * full batch).  With several ranks every rank passes its own offsets for the same nbatch batches. */
 int scs_set_active_rows(scs_problem* p, int64_t row_lo, int64_t row_hi);
 int scs_set_batches(scs_problem* p, int64_t nbatch, const int64_t* offsets);
+/* Held-out data (Problem(...; Atest, ytest), src/problems.jl:28-29): `test` is a second problem created from this
+ * rank's rows of (Atest, ytest) with the same loss.  scs_solve then records ftest(x) = model.f(Atest, ytest, x) next to
+ * every history entry (iterate.jl:169-176, utils.jl:55-57); scs_get_test_history copies them out (n = entries).  The
+ * host-driven loop simply calls scs_loss_eval on the test problem.  test = NULL detaches. */
+int scs_set_test_problem(scs_problem* p, scs_problem* test);
+int scs_get_test_history(scs_problem* p, double* out, int64_t cap, int64_t* n);
 /* Streaming-pass selection for "objective + gradient at the same x": 0 = auto (the single-pass cluster kernel
  * k_fused_grad when m <= 4096, else two passes), 1 = always two passes (k_forward + k_adjoint), 2 = fused, and
  * SCS_UNSUPPORTED if the shape has no fused kernel.  scs_get_stream_path reports what the last gradient used

@@ -414,6 +414,8 @@ class Problem:
     sol: Optional[np.ndarray] = None
     C_set: Optional[tuple] = None
     P: Optional[GroupStructure] = None
+    Atest: Optional[np.ndarray] = None  # problems.jl:28-29: held-out data, only ever used for ftest(x) (iterate.jl:169-176)
+    ytest: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.A = np.asarray(self.A, dtype=np.float64)
@@ -696,6 +698,7 @@ class Solution:  # iterate.jl:3-32
     objrel: list
     epochs: int
     iterates: list  # oracle extra: x after each step (not in the reference's Solution)
+    fvaltest: list = field(default_factory=list)  # f(Atest, ytest, x) at every recorded state (utils.jl:55-57)
 
 
 def _norm(v):
@@ -775,10 +778,15 @@ def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-1
     def push(obj, fval, pri, rel, fr):  # utils.jl:106-113
         objs.append(obj), fvals.append(fval), pris.append(pri), rels.append(rel), frels.append(fr)
 
+    test_model = model.Atest is not None and model.ytest is not None  # iterate.jl:169
+    fvaltests = []
+
     def stats(v):
         with np.errstate(all="ignore"):
             fval = float(f(v))
             obj = fval + float(get_reg(model, v, reg_name))
+            if test_model:  # show_stat! pushes ftest(x) next to every recorded state (utils.jl:55-57)
+                fvaltests.append(float(model.f.f(np.asarray(model.Atest, float), np.asarray(model.ytest, float), v)))
         return obj, fval, rel_err(v), frel(obj)
 
     for epoch_t in range(1, max_epoch + 1):  # :185
@@ -803,4 +811,4 @@ def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-1
         if _norm(x - x_prev) < x_tol * max(_norm(x_prev), 1) or f_rel_error <= f_tol or pri_res_norm < x_tol:  # :257
             break
         epochs += 1  # :261
-    return Solution(x, objs, fvals, pris, rels, frels, epochs, iterates)
+    return Solution(x, objs, fvals, pris, rels, frels, epochs, iterates, fvaltests)

@@ -211,6 +211,10 @@ struct scs_problem {
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
   double* d_u = nullptr;  // row vector of the GGN wide branch (ldd doubles, allocated on first use)
+  // held-out data (model.Atest / model.ytest): a second resident shard whose loss is recorded next to every history
+  // entry of scs_solve (ftest, iterate.jl:169-176; utils.jl:55-57)
+  scs_problem* test = nullptr;
+  std::vector<double> test_hist;
   // l-bfgs
   double *d_S = nullptr, *d_Y = nullptr;
   int64_t* d_state = nullptr;
@@ -1310,6 +1314,20 @@ extern "C" int scs_set_batches(scs_problem* p, int64_t nbatch, const int64_t* of
   for (double v : cnt) p->batch_rows_global.push_back((int64_t)(v + 0.5));
   return SCS_OK;
 }
+extern "C" int scs_set_test_problem(scs_problem* p, scs_problem* test) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (test && (test->m != p->m || test->ctx != p->ctx))
+    return fail(SCS_INVALID_ARG, "the test problem must live in the same context and have the same number of columns");
+  p->test = test;
+  return SCS_OK;
+}
+extern "C" int scs_get_test_history(scs_problem* p, double* out, int64_t cap, int64_t* n) {
+  if (!p || !n) return fail(SCS_INVALID_ARG, "NULL argument");
+  *n = (int64_t)p->test_hist.size();
+  if (out)
+    for (int64_t i = 0; i < std::min<int64_t>(cap, *n); ++i) out[i] = p->test_hist[i];
+  return SCS_OK;
+}
 extern "C" int scs_set_stream_mode(scs_problem* p, int mode) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   if (mode < 0 || mode > 2) return fail(SCS_INVALID_ARG, "stream mode must be 0 (auto), 1 (two passes) or 2 (fused)");
@@ -1657,8 +1675,20 @@ extern "C" int scs_solve(scs_problem* p, const double* x0, const double* x_star,
     *reg_out = p->h_scal[SC_REGX];
     *err2 = p->h_scal[SC_GG];
     *nx2 = p->h_scal[SC_NX2];
+    if (p->test) {  // ftest(x) = model.f(Atest, ytest, x)
+      scs_problem* q = p->test;
+      CU_TRY(cudaMemcpyAsync(q->vx[0], v.d, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      XRef tv{q->vx[0], q->next_id++};
+      SCS_TRY(ensure_loss(q, tv, SCS_WEIGHTS_NEWTON));
+      CU_TRY(cudaMemcpyAsync(q->h_scal, q->d_gl + q->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SCS_TRY(ctx_sync(c));
+      p->test_hist.push_back(fval_from_sum(q, q->h_scal[0]));
+    }
     return SCS_OK;
   };
+  p->test_hist.clear();
+  if (p->test && (p->test->m != p->m || p->test->ctx != p->ctx))
+    return fail(SCS_INVALID_ARG, "the test problem must live in the same context and have the same number of columns");
   auto rel_err = [&](double err2) {  // iterate.jl:192-197
     if (gl) return err2 / (double)m;
     return std::max(std::sqrt(err2) / std::max(nxstar, 1.0), x_tol);
@@ -1669,6 +1699,7 @@ extern "C" int scs_solve(scs_problem* p, const double* x0, const double* x_star,
     double f, r, e2, n2;
     SCS_TRY(objective_at(s, &f, &r, &e2, &n2));
     obj_star = f + r;  // iterate.jl:179
+    p->test_hist.clear();  // obj_star is not a history entry
   }
   auto frel = [&](double o) {  // iterate.jl:200 (NaN-propagating max)
     const double v = std::fabs(o - obj_star) / std::fabs(obj_star);
@@ -1701,6 +1732,8 @@ extern "C" int scs_solve(scs_problem* p, const double* x0, const double* x_star,
           SCS_TRY(set_window(p, 0, p->n, p->batch_rows_global.back()));
           SCS_TRY(objective_at(xc, &f, &r, &e2, &nx2));
           o = f + r;
+        } else if (p->test && !p->test_hist.empty()) {
+          p->test_hist.push_back(p->test_hist.back());  // same x as the entry just recorded
         }
         f_rel_error = frel(o);
         push(o, f, pri, rel_err(e2), f_rel_error);

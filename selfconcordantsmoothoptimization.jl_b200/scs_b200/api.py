@@ -170,8 +170,6 @@ class Problem:
         if any(v is not None for v in (out_fn, grad_fx, hess_fx, jac_yx, grad_fy, hess_fy)):
             raise UnsupportedError(K.SCS_UNSUPPORTED, "user derivative closures cannot run on the GPU; the built-in "
                                                       "losses carry their own out_fn and derivatives")
-        if Atest is not None or ytest is not None:
-            raise UnsupportedError(K.SCS_UNSUPPORTED, "Atest/ytest are not supported by the GPU path yet")
         self.ctx = ctx or default_context()
         self.f, self.lam, self.L, self.C_set, self.P, self.name = f, lam, L, C_set, P, name
         self.x0 = K.vec(x0)
@@ -192,6 +190,17 @@ class Problem:
             self._host = (A, yv)
             K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A), self.n, self.m, A.shape[0], K.dptr(yv),
                                                f.kind, f.param(), f.label_code(), C.byref(self._h)))
+        # held-out data: a second resident shard, only ever used for ftest(x) (iterate.jl:169-176)
+        self._test = None
+        if Atest is not None and ytest is not None:
+            self._test = Problem(Atest, ytest, self.x0, f, lam, ctx=self.ctx)
+        elif (Atest is None) != (ytest is None) and A is not None:
+            print("[ Info: Both input (Atest) and target (ytest) data are required for testing the model, but only "
+                  "one of these has been provided.\nWill skip testing...")  # iterate.jl:170-171
+
+    def ftest(self, x):
+        """model.f(Atest, ytest, x) — iterate.jl:173."""
+        return self._test.loss_eval(x, want_grad=False)[0]
 
     def reorder_rows(self, order):
         """Lay the shard out in the given row order (the data loader's one-time shuffle, utils.jl:18-25): the device
@@ -372,6 +381,9 @@ class Problem:
         return v.value
 
     def close(self):
+        if getattr(self, "_test", None) is not None:
+            self._test.close()
+            self._test = None
         if getattr(self, "_h", None):
             K.lib().scs_problem_destroy(self._h)
             self._h = C.c_void_p()
@@ -577,15 +589,22 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
         h = [np.empty(cap) for _ in range(5)]
         nh, ep = C.c_int64(), C.c_int64()
         model.set_batches(offsets)
+        test = getattr(model, "_test", None)
+        K.check(K.lib().scs_set_test_problem(model._h, test._h if test is not None else None))
         try:
             K.check(K.lib().scs_solve(model._h, K.dptr(model.x0), K.dptr(x_star), int(max_epoch), float(x_tol),
                                       float(f_tol), K.dptr(xo), *[K.dptr(a) for a in h], C.byref(nh), C.byref(ep)))
         finally:
             model.set_batches(None)
         k = nh.value
+        ftests = []
+        if test is not None:
+            buf, cnt = np.empty(cap), C.c_int64()
+            K.check(K.lib().scs_get_test_history(model._h, K.dptr(buf), cap, C.byref(cnt)))
+            ftests = list(buf[:cnt.value])
         pri = [None if np.isnan(v) else float(v) for v in h[2][:k]]
-        return Solution(xo, list(h[0][:k]), list(h[1][:k]), pri, [], list(h[3][:k]), list(h[4][:k]), {}, [], ep.value,
-                        model)
+        return Solution(xo, list(h[0][:k]), list(h[1][:k]), pri, ftests, list(h[3][:k]), list(h[4][:k]), {}, [],
+                        ep.value, model)
 
     objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
     epochs = 0
@@ -616,9 +635,14 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
         with np.errstate(all="ignore"):
             return float(np.maximum(np.abs(np.float64(o) - obj_star) / np.abs(np.float64(obj_star)), f_tol))
 
-    def push(o, f, p, r, fr):  # utils.jl:106-113
+    ftests = []
+    has_test = getattr(model, "_test", None) is not None
+
+    def push(o, f, p, r, fr, v=None):  # utils.jl:106-113 (+ show_stat!'s ftest(x), utils.jl:55-57)
         objs.append(o), fvals.append(f), pris.append(p), rels.append(r), frels.append(fr)
         times.append(time.perf_counter() - t0)
+        if has_test:
+            ftests.append(model.ftest(v))
 
     try:
         for epoch_t in range(1, int(max_epoch) + 1):
@@ -626,13 +650,13 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
             obj = fval + reg
             rel_error = rel_err(x)
             f_rel_error = frel(obj)
-            push(obj, fval, pri_res_norm, rel_error, f_rel_error)
+            push(obj, fval, pri_res_norm, rel_error, f_rel_error, x)
             for i, (lo, hi) in enumerate(windows, start=1):  # :204
                 if epoch_t == max_epoch and i == iend:  # :219-231
                     fval, reg = objective(x)
                     obj = fval + reg
                     f_rel_error = frel(obj)
-                    push(obj, fval, pri_res_norm, rel_err(x), f_rel_error)
+                    push(obj, fval, pri_res_norm, rel_err(x), f_rel_error, x)
                 if batched:
                     model.set_active_rows(lo, hi)
                 x_new, pri_res_norm = model.step(x, x_prev, epoch_t)  # :233
@@ -641,7 +665,7 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
                         fval, reg = objective(x_new)
                         obj = fval + reg
                         f_rel_error = frel(obj)
-                        push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error)
+                        push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error, x_new)
                     x_prev, x = x.copy(), x_new
                     epochs += 1
                     break
@@ -652,7 +676,7 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
     finally:
         if batched:
             model.set_active_rows(0, model.n)
-    return Solution(x, objs, fvals, pris, [], rels, frels, {}, times, epochs, model)
+    return Solution(x, objs, fvals, pris, ftests, rels, frels, {}, times, epochs, model)
 
 
 def batch_shard(n, world, rank, batch_size, local_max_iter=None, perm=None):

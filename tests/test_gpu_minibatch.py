@@ -130,3 +130,23 @@ def test_active_rows_components(scs):
                 tol = 2e-12 if mode == "dmma" else max(2e-12, 5e-11 / np.sqrt(max(hi - lo, 1)))
                 assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= tol or hi - lo < 2
     p.close()
+
+
+@pytest.mark.parametrize("device_loop", [False, True])
+@pytest.mark.parametrize("batch_size", [None, 1500])
+def test_held_out_data_history(scs, device_loop, batch_size):
+    """Problem(...; Atest, ytest): Solution.fvaltest holds f(Atest, ytest, x) for every recorded state
+    (iterate.jl:169-176, utils.jl:55-57), full batch and mini-batch, host loop and in-library loop."""
+    name = "c3_logreg_lqn_l1"
+    A, y, x0 = cases.data(name)
+    At, yt = A[:777] * 1.5, y[:777]
+    mo, modelo, reg, ho, kw = cases.build(name, O, Atest=At, ytest=yt)
+    kw = dict(kw, max_epoch=6)
+    so = O.iterate(mo, modelo, reg, ho, batch_size=batch_size, **kw)
+    mg, modelg, reg, hg, _ = cases.build(name, scs, Atest=At, ytest=yt)
+    sg = scs.iterate(mg, modelg, reg, hg, verbose=0, device_loop=device_loop, batch_size=batch_size, shuffle_batch=False,
+                     **kw)
+    assert len(so.fvaltest) == len(so.obj) and len(sg.fvaltest) == len(sg.obj) == len(so.obj)
+    assert hist_err(sg.fvaltest, so.fvaltest) <= TOL
+    assert hist_err(sg.obj, so.obj) <= TOL and relerr(sg.x, so.x) <= TOL
+    modelg.close()
