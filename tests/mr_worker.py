@@ -63,6 +63,32 @@ def main():
         dist.all_gather(lst, t)
         assert all(torch.equal(lst[0], u) for u in lst), name
         model.close()
+    # ---- mini-batches across ranks: every (shuffled) batch is split over the ranks, each rank uploads its slices
+    # batch after batch and steps through its local offsets; held-out rows are sharded the same way
+    name = "c3_logreg_lqn_l1"
+    A, y, x0 = cases.data(name)
+    n = A.shape[0]
+    perm = np.random.default_rng(9).permutation(n)
+    At, yt = A[:600] * 1.25, y[:600]
+    for mname, bs in (("ProxLQNSCORE", 700), ("ProxGGNSCORE", 1100)):
+        loss_o = O.LogisticLoss(1 / n, "consistent")
+        loss_g = S.LogisticLoss(1 / n, "consistent")
+        so = O.iterate(getattr(O, mname)(), O.Problem(A, y, x0, loss_o, 1e-2, Atest=At, ytest=yt), "l1",
+                       O.PHuberSmootherL1L2(1.0), max_epoch=4, alpha=1, batch_size=bs, shuffle_batch=True, perm=perm,
+                       local_max_iter=3)
+        rows, loc = S.batch_shard(n, world, rank, bs, local_max_iter=3, perm=perm)
+        t0, tl = S.shard_rows(600, world, rank)
+        for dl in (False, True):
+            model = S.Problem(A[rows], y[rows], x0, loss_g, 1e-2, ctx=ctx, Atest=At[t0:t0 + tl], ytest=yt[t0:t0 + tl])
+            sg = S.iterate(getattr(S, mname)(), model, "l1", S.PHuberSmootherL1L2(1.0), max_epoch=4, alpha=1,
+                           verbose=0, device_loop=dl, batch_offsets=loc)
+            ex = np.linalg.norm(sg.x - so.x) / np.linalg.norm(so.x)
+            eo = max(abs(a - b) / abs(b) for a, b in zip(sg.obj, so.obj))
+            et = max(abs(a - b) / abs(b) for a, b in zip(sg.fvaltest, so.fvaltest))
+            assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj) == len(sg.fvaltest), (mname, dl)
+            assert ex <= 1e-10 and eo <= 1e-10 and et <= 1e-10, (mname, dl, rank, ex, eo, et)
+            worst = max(worst, ex, eo, et)
+            model.close()
     dist.barrier()
     if rank == 0:
         print(f"MULTIRANK_OK world={world} worst_rel_err={worst:.3e}")
