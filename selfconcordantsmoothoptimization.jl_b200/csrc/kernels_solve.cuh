@@ -264,62 +264,85 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
       }
 }
 
-// Loads the factored diagonal block k into shared memory Ls[r][c] (lower part, zero above), 256 threads.
-SCS_DEVINL void load_diag_block(double* Ls, const double* __restrict__ M, int64_t ld, int k0, int nb, int tid) {
-  const int r = tid & 63, cb = tid >> 6;
-  double v[16];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int c = cb + 4 * u;
-    v[u] = (r < nb && c < nb && c <= r) ? M[(int64_t)(k0 + c) * ld + k0 + r] : 0.0;
+// ---- backward substitution  L' d = y  in two launches ----------------------------------------------------------
+// k_invdiag: Wt_k = (L_kk^-1)' for every 64x64 diagonal block at once (one CTA per block; thread j builds column j of
+// L_kk^-1 by forward substitution, all 64 columns in parallel).  Stored as Wt[k][c][r] = (L_kk^-1)[r][c].
+__global__ void __launch_bounds__(64) k_invdiag(const double* __restrict__ M, int64_t ld, int m,
+                                                double* __restrict__ Wt) {
+  __shared__ double Ws[kNB * kLS];  // Ws[p][j] = (L^-1)[p][j]
+  const int k0 = blockIdx.x * kNB, nb = min(kNB, m - k0), j = threadIdx.x;
+  const double* Lb = M + (int64_t)k0 * ld + k0;  // L[i][p] = Lb[p*ld + i] (a broadcast read: same address in every lane)
+  for (int i = 0; i < kNB; ++i) {  // row i of L^-1; thread j owns column j (zero above the diagonal)
+    double acc = 0.0;
+    if (i < nb) {
+      for (int p = 0; p < i; ++p) acc = fma(__ldg(Lb + (int64_t)p * ld + i), Ws[p * kLS + j], acc);  // Ws[p][j] = 0 for p < j
+      Ws[i * kLS + j] = ((i == j ? 1.0 : 0.0) - acc) / __ldg(Lb + (int64_t)i * ld + i);
+    } else {
+      Ws[i * kLS + j] = i == j ? 1.0 : 0.0;  // ragged last block: identity padding
+    }
   }
-#pragma unroll
-  for (int u = 0; u < 16; ++u) Ls[r * kLS + cb + 4 * u] = v[u];
+  __syncthreads();
+  double* out = Wt + (int64_t)blockIdx.x * kNB * kNB;
+  for (int e = j; e < kNB * kNB; e += 64) {
+    const int r = e & 63, c = e >> 6;
+    out[c * kNB + r] = Ws[r * kLS + c];
+  }
 }
 
-// Backward substitution step for block k (L' d = y), right-looking: solve L_kk' d_k = y_k, then for every column
-// j < k0: y_j -= sum_{r in block k} L[r, j] d_r.
-__global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ M, int64_t ld, int m, int k0,
-                                                  const double* __restrict__ rdiag_g, double* __restrict__ y,
-                                                  double* __restrict__ d) {
-  __shared__ double Ls[kNB * kLS];
-  __shared__ double yk[kNB], dk[kNB], rd[kNB];
-  const int nb = min(kNB, m - k0);
-  const int tid = threadIdx.x;
-  load_diag_block(Ls, M, ld, k0, nb, tid);
-  if (tid < kNB) {
-    yk[tid] = tid < nb ? y[k0 + tid] : 0.0;
-    rd[tid] = tid < nb ? rdiag_g[k0 + tid] : 0.0;
-    dk[tid] = 0.0;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    for (int c = nb - 1; c >= 0; --c) {
-      const double dc = yk[c] * rd[c];
-      if (tid == 0) dk[c] = dc;
-      const int r0 = tid, r1 = tid + 32;
-      if (r0 < c) yk[r0] -= Ls[c * kLS + r0] * dc;  // (L')[r][c] = L[c][r]
-      if (r1 < c) yk[r1] -= Ls[c * kLS + r1] * dc;
-      __syncwarp();
+// k_bwd_all: one persistent kernel, gridDim.x <= number of SMs (all CTAs co-resident; cooperative launch).  For block
+// k = nblk-1 .. 0: every CTA waits until all updates of y_k have landed (grid barrier = one global counter), forms
+// d_k = Wt_k y_k itself (64x64 mat-vec, redundant but parallel), then applies  y_j -= L[block k, j]' d_k  to its own
+// columns j < k0 (64 columns per CTA and sweep, 4 threads per column).
+__global__ void __launch_bounds__(256) k_bwd_all(const double* __restrict__ M, int64_t ld, int m,
+                                                 const double* __restrict__ Wt, double* __restrict__ y,
+                                                 double* __restrict__ d, unsigned long long* __restrict__ bar) {
+  __shared__ double yk[kNB], dk[kNB];
+  const int nblk = (m + kNB - 1) / kNB;
+  const int tid = threadIdx.x, c = tid >> 2, q = tid & 3;
+  unsigned long long want = 0;
+  for (int k = nblk - 1; k >= 0; --k) {
+    const int k0 = k * kNB, nb = min(kNB, m - k0);
+    if (tid == 0 && want > 0) {  // every CTA has finished the previous block's updates
+      const long long t0 = clock64();
+      while (true) {
+        unsigned long long seen;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+        if (seen >= want) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
     }
-  }
-  __syncthreads();
-  const int col = blockIdx.x * 256 + tid;
-  if (col < k0) {
-    const double* colp = M + (int64_t)col * ld + k0;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    int r = 0;
-    for (; r + 16 <= nb; r += 16) {
-      double v[16];
+    __syncthreads();
+    if (tid < kNB) yk[tid] = tid < nb ? __ldcg(y + k0 + tid) : 0.0;
+    __syncthreads();
+    {  // d_k[c] = sum_r (L_kk^-1)[r][c] y_k[r] = sum_r Wt[c][r] y_k[r]
+      const double* w = Wt + (int64_t)k * kNB * kNB + c * kNB + 16 * q;
+      double acc = 0.0;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = colp[r + u];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) s[u & 3] = fma(v[u], dk[r + u], s[u & 3]);
+      for (int i = 0; i < 16; ++i) acc = fma(w[i], yk[16 * q + i], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (q == 0) dk[c] = c < nb ? acc : 0.0;
     }
-    for (; r < nb; ++r) s[0] = fma(colp[r], dk[r], s[0]);
-    y[col] -= (s[0] + s[1]) + (s[2] + s[3]);
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < nb) d[k0 + tid] = dk[tid];
+    for (int col0 = blockIdx.x * kNB; col0 < k0; col0 += gridDim.x * kNB) {
+      const int col = col0 + c;  // col < k0 <= m always (k0 is a multiple of 64)
+      const double* lp = M + (int64_t)col * ld + k0 + 16 * q;
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (16 * q + i < nb) acc = fma(lp[i], dk[16 * q + i], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (q == 0) y[col] -= acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar, 1ULL);
+    }
+    want += gridDim.x;
   }
-  if (blockIdx.x == 0 && tid < nb) d[k0 + tid] = dk[tid];
 }
 
 // ---- ProxGGNSCORE underdetermined branch (n+1 <= m, prox-GGN-SCORE.jl:124-127) ----------------------------------

@@ -519,7 +519,7 @@ static int gram_setup(scs_problem* p) {
   SCS_TRY(dalloc(&p->d_G, (size_t)m * m));
   SCS_TRY(dalloc(&p->d_Gsave, (size_t)m * m));
   const int nblk = (int)((m + kNB - 1) / kNB);
-  SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB));
+  SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16));  // 1/L_jj | inverted diagonal blocks | barrier
   CU_TRY(cudaMalloc((void**)&p->d_info, sizeof(int)));
   if (p->loss.kind != SCS_LOSS_QUADFORM) {
     GramPlan& pl = p->plan;
@@ -773,7 +773,7 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
       // same shared-memory carve-out for every kernel of the sequence: no SM reconfiguration between launches
       CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CU_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_bwd_step, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_bwd_all, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr_set = true;
     }
   }
@@ -796,9 +796,21 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   CU_TRY(cudaStreamSynchronize(c->stream));
   if (info == 0) {
     // tmp now holds y
-    for (int k = nblk - 1; k >= 0; --k) {
-      const int k0 = k * kNB;
-      LAUNCH(c, k_bwd_step, std::max(1, (k0 + 255) / 256), 256, 0, M, (int64_t)m, m, k0, rdiag, tmp, dsol);
+    // backward substitution: invert the diagonal blocks (all at once), then one persistent kernel for the sweep
+    double* Wt = Linv + round_up(m, 16);
+    unsigned long long* bar = (unsigned long long*)(Wt + (size_t)nblk * kNB * kNB);
+    LAUNCH(c, k_invdiag, nblk, 64, 0, (const double*)M, (int64_t)m, m, Wt);
+    CU_TRY(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), c->stream));
+    {
+      int grid = std::min(c->num_sms, nblk);
+      const double* Mc = M;
+      int64_t ldm = m;
+      int mm = m;
+      const double* Wc = Wt;
+      void* args[] = {(void*)&Mc, (void*)&ldm, (void*)&mm, (void*)&Wc, (void*)&tmp, (void*)&dsol, (void*)&bar};
+      cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_bwd_all, dim3(grid), dim3(256), args, 0, c->stream);
+      c->launches += 1;
+      if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_bwd_all launch: ") + cudaGetErrorString(le));
     }
     *used_fallback = 0;
     return SCS_OK;
@@ -1837,7 +1849,7 @@ extern "C" int scs_linear_solve(scs_ctx* c, const double* M, const double* b, in
     dfree(dM), dfree(dS), dfree(dL), dfree(db), dfree(dt), dfree(dd), dfree(di);
   };
   if ((rc = dalloc(&dM, (size_t)m * m)) || (rc = dalloc(&dS, (size_t)m * m)) ||
-      (rc = dalloc(&dL, (size_t)nblk * kNB * kNB)) || (rc = dalloc(&db, m)) || (rc = dalloc(&dt, m)) ||
+      (rc = dalloc(&dL, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16)) || (rc = dalloc(&db, m)) || (rc = dalloc(&dt, m)) ||
       (rc = dalloc(&dd, m))) {
     cleanup();
     return rc;
