@@ -455,6 +455,287 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
   }
 }
 
+// ---- 2-CTA variant (opt-in: SCS_I8_2CTA=1; parity-tested, measured equal to k_i8syrk under the 1 kW power cap) ---
+// Motivation: in k_i8syrk the shared-memory port is busier than the tensor pipe: at full rate a 128x256x32 UMMA (135 cycles)
+// reads 12 KB of operands and its share of the TMA fill is another 12 KB — 178 B/cycle against the SM's 128 B/cycle,
+// which caps the IMMA pipe at 72 % (ncu: 71.7 % active).  In cta_group::2 mode the two CTAs of a pair (ranks 2p, 2p+1
+// of the cluster) issue one 256x256x32 UMMA: each CTA supplies its own 128 rows of A and HALF of the B slab
+// (128 columns of G), so fill and reads per SM drop to 8 + 8 KB per UMMA (118 B/cycle).
+//   * cluster of 4 = two pairs stacked vertically (512 rows x 256 columns of G, as before);
+//   * B half q (= rank & 1) is needed by ranks q and q+2: each of them fetches 64 of its 128 rows and multicasts to both;
+//   * only the pair leader (even rank) issues tcgen05.mma.cta_group::2; the peer's MMA warp relays "my stage is full"
+//     to the leader's pfull barrier (remote mbarrier arrive); tcgen05.commit.cta_group::2 multicasts the stage release to
+//     all four CTAs (both leaders must be done before a slot is refilled) and the accumulator hand-off to the pair;
+//   * epilogue warps of both CTAs drain their own 128 TMEM lanes and arrive on the LEADER's acc_empty barrier.
+// bounded wait: a protocol error in the pair hand-shakes traps (launch error) instead of hanging the device
+SCS_DEVINL void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (ok) return;
+    if (t0 == 0)
+      t0 = clock64();
+    else if (clock64() - t0 > 6000000000LL)
+      __trap();
+  }
+}
+constexpr int kI8Stages2 = 6;
+constexpr int kI8BHalf = kI8BN / 2;                       // B rows (columns of G) held by one CTA of a pair
+constexpr int kI8Stage2Bytes = kI8ABytes + kI8BHalf * kI8BK;  // 16 + 16 KB
+constexpr int kI8Smem2Bytes = kI8Stages2 * kI8Stage2Bytes + 1024 + 512;
+constexpr uint32_t kI8Idesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kI8BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+SCS_DEVINL void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+SCS_DEVINL void tc_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+SCS_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {  // arrive on the same barrier in CTA `rank`
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// Control-only signal (the data it announces was written by TMA into this CTA's own shared memory and is consumed by
+// this SM's tensor core): relaxed, so that no cluster-scope fence (ERRBAR + CCTL.IVALL) is paid per pipeline stage.
+SCS_DEVINL void mbar_arrive_remote_relaxed(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
+__global__ void __launch_bounds__(kI8Threads, 1)
+k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap bmap, I8Plan pl,
+          const int2* __restrict__ tiles, int8_t* __restrict__ partial /* [nmod][nchunks][m][ldp] */,
+          unsigned long long* __restrict__ progress /* zeroed before the launch */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = (uint64_t*)(smem + kI8Stages2 * kI8Stage2Bytes);
+  uint64_t* empty = full + kI8Stages2;
+  uint64_t* pfull = empty + kI8Stages2;  // leader only: the peer's stage is full
+  uint64_t* acc_full = pfull + kI8Stages2;
+  uint64_t* acc_empty = acc_full + 2;    // leader only: both CTAs' epilogues have drained the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int q = crank & 1;           // position inside the pair = which half of the B slab this CTA holds
+  const int leader_rank = crank & ~1;
+  const bool is_leader = q == 0;
+  const int64_t cid = blockIdx.x / kI8Cluster, ncl = gridDim.x / kI8Cluster;
+  constexpr uint16_t kMaskAll = (uint16_t)((1u << kI8Cluster) - 1u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kI8Stages2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kI8Cluster / 2);  // one tcgen05.commit arrival from each pair leader of the cluster
+      mbar_init(&pfull[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);  // 4 epilogue warps of each CTA of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation for the pair: one warp of each CTA
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kI8TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (lock-step with the other clusters, as in k_i8syrk) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int64_t steps = (pl.units + ncl - 1) / ncl;
+      const int segs = (int)((pl.chunk_kblocks + kI8SegKb - 1) / kI8SegKb);
+      const unsigned long long ncta = gridDim.x;
+      bool in_step = true;
+      const int h = crank >> 1;  // which 64 of the 128 rows of its B half this CTA fetches
+      const uint16_t bmask = (uint16_t)((1u << q) | (1u << (q + 2)));  // the two CTAs that hold half q
+      for (int64_t st = 0; st < steps; ++st) {
+        const int64_t u = cid + st * ncl;
+        const bool valid = u < pl.units;
+        int l = 0, c = 0, t = 0;
+        if (valid) i8_unit(pl, u, l, c, t);
+        const int2 tile = valid ? tiles[t] : make_int2(0, 0);
+        const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
+        const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
+        for (int sg = 0; sg < segs; ++sg) {
+          const unsigned long long point = (unsigned long long)(st * segs + sg);
+          if (point > 0) {
+            atomicAdd(progress, 1ULL);
+            if (in_step) {
+              const unsigned long long want = point * ncta;
+              int spins = 0;
+              while (true) {
+                unsigned long long seen;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(progress) : "memory");
+                if (seen >= want) break;
+                if (++spins > 40000) {
+                  in_step = false;
+                  break;
+                }
+                __nanosleep(100);
+              }
+            }
+          }
+          if (!valid) continue;
+          const int64_t s0 = kb0 + (int64_t)sg * kI8SegKb;
+          const int64_t s1 = s0 + kI8SegKb < kb1 ? s0 + kI8SegKb : kb1;
+          for (int64_t kb = s0; kb < s1; ++kb) {
+            mbar_wait_bounded(&empty[stage], phase ^ 1);  // both pairs of the cluster have consumed this slot
+            mbar_expect_tx(&full[stage], kI8Stage2Bytes);
+            uint8_t* sa = smem + stage * kI8Stage2Bytes;
+            tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
+            tma_load_3d_mc(sa + kI8ABytes + h * (kI8BPart * kI8BK), &bmap, &full[stage], (int)(kb * kI8BK),
+                           tile.y * kI8BN + q * kI8BHalf + h * kI8BPart, l, bmask);
+            if (++stage == kI8Stages2) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      if (is_leader) {
+        // ===== MMA issuer for the pair (one thread) =====
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
+        for (int64_t u = cid; u < pl.units; u += ncl) {
+          int l, c, t;
+          i8_unit(pl, u, l, c, t);
+          const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
+          const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
+          mbar_wait_bounded(&acc_empty[as], aphase ^ 1);  // both epilogues have drained this accumulator
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(as * kI8BN);
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            mbar_wait_bounded(&full[stage], phase);
+            mbar_wait_bounded(&pfull[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kI8Stage2Bytes);
+            const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kI8ABytes);
+#pragma unroll
+            for (int k = 0; k < kI8BK / 32; ++k)
+              umma2_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kI8Idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+            tc_commit2_mc(&empty[stage], kMaskAll);
+            if (++stage == kI8Stages2) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit2_mc(&acc_full[as], pair_mask);  // accumulator complete: wake the epilogues of both CTAs
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+        }
+      } else {
+        // ===== peer: tell the leader when this CTA's half of the stage has landed =====
+        uint32_t pf_remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pf_remote) : "r"(smem_u32(pfull)), "r"((uint32_t)leader_rank));
+        for (int64_t u = cid; u < pl.units; u += ncl) {
+          int l, c, t;
+          i8_unit(pl, u, l, c, t);
+          const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
+          const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            mbar_wait_bounded(&full[stage], phase);
+            mbar_arrive_remote_relaxed(pf_remote + 8u * (uint32_t)stage);
+            if (++stage == kI8Stages2) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> mod p -> int8 partial residues =====
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t u = cid; u < pl.units; u += ncl) {
+      int l, c, t;
+      i8_unit(pl, u, l, c, t);
+      const int2 tile = tiles[t];
+      const int p = c_mod_p[l];
+      const double pd = (double)p, ip = 1.0 / pd;
+      mbar_wait_bounded(&acc_full[as], aphase);
+      tc_fence_after();
+      const int jc = (tile.x * kI8Cluster + crank) * kI8BM + row_in_tile;
+      int8_t* prow = partial + (((int64_t)l * pl.nchunks + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
+      const uint32_t taddr = tmem_base + (uint32_t)(as * kI8BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < kI8BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+        uint32_t packed[8];
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int bq = 0; bq < 4; ++bq) {
+            const double dv = (double)(int)v[4 * qq + bq];
+            int r = (int)fma(-rint(dv * ip), pd, dv);
+            if (2 * r >= p) r -= p;
+            if (2 * r < -p) r += p;
+            word |= (uint32_t)(r & 0xff) << (8 * bq);
+          }
+          packed[qq] = word;
+        }
+        const int kc0 = tile.y * kI8BN + cc * 32;
+        if (jc < pl.m && kc0 < pl.ldp) {
+          uint4* d4 = reinterpret_cast<uint4*>(prow + cc * 32);
+          d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (kc0 + 16 < pl.ldp) d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader)
+          mbar_arrive(&acc_empty[as]);
+        else
+          mbar_arrive_remote(&acc_empty[as], (uint32_t)leader_rank);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kI8TmemCols) : "memory");
+  }
+}
+
 // ---- CRT reconstruction -----------------------------------------------------------------------------------------
 // For each lower-triangle (jc >= kc): R = CRT({sum_c partial[l][c][jc][kc] mod p_l}) in (-P/2, P/2), then
 // G[jc,kc] = G[kc,jc] = R * 2^(e_jc + e_kc - 2b).  One thread reconstructs 4 consecutive kc (32-bit loads of the

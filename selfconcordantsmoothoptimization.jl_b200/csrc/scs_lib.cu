@@ -631,6 +631,7 @@ static int i8_setup(scs_problem* p) {
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (int8 B slab) failed: " + std::to_string((int)r));
   CU_TRY(cudaFuncSetAttribute(k_i8syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes));
+  CU_TRY(cudaFuncSetAttribute(k_i8syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8Smem2Bytes));
   {
     StageTimer t(c, ST_FWD);
     LAUNCH(c, k_colabsmax, (unsigned)m, 256, 0, p->dA, p->ldd, p->n, (int)m, p->d_colmax);
@@ -684,10 +685,16 @@ static int run_gram_i8(scs_problem* p, int* done) {
   }
   {
     StageTimer t(c, ST_GRAM);
+    // SCS_I8_2CTA=1 selects the cta_group::2 SYRK (kernels_i8gram.cuh).  Measured equal to the 1-CTA kernel on this part
+    // (C2: 104.0 vs 104.9 ms, both power-capped at 1.56 GHz; 400k x 2048: 11.1 vs 10.6 ms), so the default stays 1-CTA.
+    static const bool two_cta = []() {
+      const char* e = getenv("SCS_I8_2CTA");
+      return e && e[0] == '1';
+    }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(c->num_sms / kI8Cluster * kI8Cluster));
     cfg.blockDim = dim3(kI8Threads);
-    cfg.dynamicSmemBytes = kI8SmemBytes;
+    cfg.dynamicSmemBytes = two_cta ? kI8Smem2Bytes : kI8SmemBytes;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -699,14 +706,18 @@ static int run_gram_i8(scs_problem* p, int* done) {
     // persistent kernel: exactly as many clusters as can be co-resident (GPC shapes strand some SMs for clusters of 4)
     if (p->i8_clusters == 0) {
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg) != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
+      cudaError_t oe = two_cta ? cudaOccupancyMaxActiveClusters(&nc, k_i8syrk2, &cfg)
+                               : cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg);
+      if (oe != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
       p->i8_clusters = nc;
     }
     const int ncl = (int)std::min<int64_t>(p->i8_clusters, pl.units);
     cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
     CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
-    cudaError_t le = cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
-                                        p->d_i8partial, p->d_i8progress);
+    cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
+                                                  p->d_i8partial, p->d_i8progress)
+                             : cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
+                                                  p->d_i8partial, p->d_i8progress);
     c->launches += 1;
     if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
   }
