@@ -1098,6 +1098,57 @@ extern "C" int scs_problem_create(scs_ctx* ctx, const double* A, int64_t n_local
   return SCS_OK;
 }
 
+extern "C" int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                                      int64_t index_base, int64_t n_local, int64_t m, const double* y, int loss_kind,
+                                      double loss_param, int label_mode, scs_problem** out) {
+  if (!colptr || !y) return fail(SCS_INVALID_ARG, "colptr or y is NULL");
+  if (index_base != 0 && index_base != 1) return fail(SCS_INVALID_ARG, "index_base must be 0 or 1");
+  if (m < 1) return fail(SCS_INVALID_ARG, "n_local and m must be positive");
+  const int64_t nnz = colptr[m] - colptr[0];
+  if (colptr[0] != index_base || nnz < 0) return fail(SCS_INVALID_ARG, "malformed colptr");
+  for (int64_t j = 0; j < m; ++j)
+    if (colptr[j + 1] < colptr[j]) return fail(SCS_INVALID_ARG, "colptr must be non-decreasing");
+  if (nnz > 0 && (!rowval || !nzval)) return fail(SCS_INVALID_ARG, "rowval or nzval is NULL");
+  int s = problem_alloc(ctx, n_local, m, loss_kind, loss_param, label_mode, out);
+  if (s != SCS_OK) {
+    if (out && *out) {
+      scs_problem_destroy(*out);
+      *out = nullptr;
+    }
+    return s;
+  }
+  scs_problem* p = *out;
+  int64_t *d_cp = nullptr, *d_rv = nullptr;
+  double* d_nz = nullptr;
+  int* d_bad = nullptr;
+  int bad = 0;
+  cudaError_t e = cudaMalloc((void**)&d_cp, (m + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_rv, std::max<int64_t>(nnz, 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_nz, std::max<int64_t>(nnz, 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_cp, colptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_rv, rowval, nnz * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_nz, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->dy, y, n_local * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    k_scatter_csc<<<(unsigned)std::min<int64_t>(m, 4096), 256, 0, ctx->stream>>>(d_cp, d_rv, d_nz, index_base, n_local, (int)m,
+                                                                              p->ldd, p->dA, d_bad);
+    ctx->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dfree(d_cp), dfree(d_rv), dfree(d_nz), dfree(d_bad);
+  if (e != cudaSuccess || bad) {
+    scs_problem_destroy(p);
+    *out = nullptr;
+    if (bad) return fail(SCS_INVALID_ARG, "rowval entry outside 1..n_local");
+    return fail(e == cudaErrorMemoryAllocation ? SCS_OOM : SCS_CUDA_ERROR, std::string("CSC upload failed: ") + cudaGetErrorString(e));
+  }
+  return SCS_OK;
+}
+
 extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64_t row0, int64_t n_local, int64_t m,
                                             int loss_kind, double loss_param, int label_mode, uint64_t seed,
                                             double density, scs_problem** out) {

@@ -78,4 +78,21 @@ __global__ void k_synth_y(double* __restrict__ y, const double* __restrict__ z, 
   }
 }
 
+// Expands a CSC shard (Julia SparseMatrixCSC: colptr / rowval / nzval, index base 0 or 1) into the zero-initialised
+// dense column-major resident layout.  One CTA per column (grid-stride), threads over that column's stored entries.
+__global__ void k_scatter_csc(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                              const double* __restrict__ nzval, int64_t base, int64_t n, int m, int64_t ldd,
+                              double* __restrict__ A, int* __restrict__ bad) {
+  for (int j = blockIdx.x; j < m; j += gridDim.x) {
+    const int64_t p0 = colptr[j] - base, p1 = colptr[j + 1] - base;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const int64_t i = rowval[p] - base;
+      if (i < 0 || i >= n)
+        atomicExch(bad, 1);
+      else
+        A[(int64_t)j * ldd + i] = nzval[p];
+    }
+  }
+}
+
 }  // namespace scs

@@ -16,7 +16,7 @@ using SelfConcordantSmoothOptimization
 import SelfConcordantSmoothOptimization: iterate!, ProximalMethod, ProxNSCORE, ProxGGNSCORE, ProxLQNSCORE,
     Problem, Solution, PHuberSmootherL1L2, PHuberSmootherIndBox, PHuberSmootherGL, ExponentialSmootherIndBox,
     LogExpSmootherIndBox, OsBaSmootherL1L2, OsBaSmootherGL, bounds_sanity_check
-using LinearAlgebra, Dates, Random
+using LinearAlgebra, Dates, Random, SparseArrays
 
 export LogisticLoss, LeastSquaresLoss, QuadFormLoss, GPUContext, gpu_iterate!
 
@@ -82,13 +82,21 @@ function GPUProblem(ctx::GPUContext, model)
     any(x -> x !== nothing, (model.grad_fx, model.hess_fx, model.jac_yx, model.grad_fy, model.hess_fy)) &&
         Base.error("scs_b200: user derivative closures cannot run on the GPU")
     (model.out_fn !== nothing) && @info "out_fn is ignored: the built-in loss carries its own model output function"
-    A = Matrix{Float64}(model.A)
     y = Vector{Float64}(vec(model.y))
-    n, m = size(A)
+    n, m = size(model.A)
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve A y check(ccall((:scs_problem_create, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
-        ctx.h, A, n, m, stride(A, 2), y, code, param, lmode, out))
+    if model.A isa SparseMatrixCSC   # README.md:105 builds A with sprandn: only the stored entries cross PCIe
+        S = SparseMatrixCSC{Float64,Int64}(model.A)
+        colptr, rowval, nzval = S.colptr, S.rowval, S.nzval
+        GC.@preserve colptr rowval nzval y check(ccall((:scs_problem_create_csc, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint,
+             Ref{Ptr{Cvoid}}), ctx.h, colptr, rowval, nzval, 1, n, m, y, code, param, lmode, out))
+    else
+        A = Matrix{Float64}(model.A)
+        GC.@preserve A y check(ccall((:scs_problem_create, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
+            ctx.h, A, n, m, stride(A, 2), y, code, param, lmode, out))
+    end
     p = GPUProblem(out[], m, ctx)
     finalizer(x -> ccall((:scs_problem_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
     return p

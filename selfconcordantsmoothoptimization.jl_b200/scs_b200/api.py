@@ -177,6 +177,20 @@ class Problem:
         self._h = C.c_void_p()
         self._reg_name = None
         self._host = None  # (A, y) as given: needed again only if iterate!(shuffle_batch=true) reorders the rows
+        if A is not None and hasattr(A, "tocsc"):  # scipy.sparse (the README builds A with sprandn): CSC over the wire
+            Ac = A.tocsc().astype(np.float64)
+            Ac.sum_duplicates()
+            yv = K.vec(y, Ac.shape[0])
+            if Ac.shape[1] != self.x0.shape[0]:
+                raise ValueError("x0 length must equal the number of columns of A")
+            self.n, self.m = Ac.shape
+            cp = np.ascontiguousarray(Ac.indptr, dtype=np.int64)
+            rv = np.ascontiguousarray(Ac.indices, dtype=np.int64)
+            nz = np.ascontiguousarray(Ac.data, dtype=np.float64)
+            self._host = (Ac, yv)
+            K.check(K.lib().scs_problem_create_csc(self.ctx._h, K.iptr(cp), K.iptr(rv), K.dptr(nz), 0, self.n, self.m,
+                                                   K.dptr(yv), f.kind, f.param(), f.label_code(), C.byref(self._h)))
+            A = None
         if A is not None:
             A = np.asarray(A, dtype=np.float64)
             if A.ndim != 2:
@@ -210,6 +224,8 @@ class Problem:
                                                       "problem from host arrays or pass shuffle_batch=False")
         A, yv = self._host
         order = np.asarray(order, dtype=np.int64)
+        if hasattr(A, "tocsc"):
+            A = A.toarray()
         A2 = np.asfortranarray(A[order])
         y2 = np.ascontiguousarray(yv[order])
         K.lib().scs_problem_destroy(self._h)

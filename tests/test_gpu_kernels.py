@@ -312,3 +312,29 @@ def test_gram_i8_vs_dmma_bitwise_reproducible(scs):
     d = np.sqrt(np.diag(Gd))
     assert np.max(np.abs(G1 - Gd) / np.outer(d, d)) <= 2e-12
     p.close()
+
+
+def test_gram_i8_two_cta_variant():
+    """The opt-in cta_group::2 SYRK (SCS_I8_2CTA=1, read once per process) gives bit-identical integer Grams."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import scs_b200 as S\nfrom oracle import synth\n"
+        "n, m = 70001, 300\n"
+        "p = S.Problem.synthetic(n, m, S.LogisticLoss(1 / n, 'consistent'), 1e-3)\n"
+        "p.set_gram_mode('i8'); x = synth.make_x0(m) * 0.3\n"
+        "G = p.gram(x, weights='ggn'); assert p.gram_path() == 'i8'\n"
+        "np.save(sys.argv[1], G)\n" % (root, os.path.join(root, "selfconcordantsmoothoptimization.jl_b200")))
+    outs = []
+    for flag in ("0", "1"):
+        out = os.path.join(root, "gpurun_out", f"_g2cta_{flag}.npy")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        env = dict(os.environ, SCS_I8_2CTA=flag)
+        r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out))
+        os.remove(out)
+    assert np.array_equal(outs[0], outs[1])

@@ -213,3 +213,28 @@ def test_ggn_wide_branch(scs, n, m, loss, ss_type):
         assert hist_err(sg.obj, so.obj) <= 1e-9
         assert np.array_equal(sg.x != 0, so.x != 0)
         pg.close()
+
+
+def test_sparse_csc_input(scs):
+    """README.md:100-125: A = sprandn(n, m, 0.01).  A scipy CSC matrix goes over the wire as colptr / rowval / nzval
+    (scs_problem_create_csc) and must give exactly what the dense upload gives."""
+    import scipy.sparse as sp
+    A, y, x0 = cases.data("c1_readme_logreg_n")  # 1 %-dense look-alike of the README example
+    rng = np.random.default_rng(3)
+    A = A + (rng.random(A.shape) < 0.05) * rng.standard_normal(A.shape)  # a few more entries per column
+    so = O.iterate(O.ProxNSCORE(), O.Problem(A, y, x0, O.LogisticLoss(1 / 50), 1e-1), "l1", O.PHuberSmootherL1L2(1.0),
+                   max_epoch=30, x_tol=1e-6, f_tol=1e-6)
+    sols = []
+    for mat in (A, sp.csc_matrix(A), sp.csr_matrix(A)):
+        p = scs.Problem(mat, y, x0, scs.LogisticLoss(1 / 50), 1e-1)
+        sols.append(scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=30, x_tol=1e-6,
+                                f_tol=1e-6, verbose=0))
+        p.close()
+    for sg in sols:
+        assert sg.epochs == so.epochs and relerr(sg.x, so.x) <= TOL and hist_err(sg.obj, so.obj) <= TOL
+    assert np.array_equal(sols[0].x, sols[1].x) and np.array_equal(sols[0].x, sols[2].x)  # same resident matrix
+    with pytest.raises(scs.ScsError):  # malformed structure is an argument error, not a crash
+        bad = sp.csc_matrix(A)
+        bad.indices = bad.indices.copy()
+        bad.indices[0] = A.shape[0] + 7
+        scs.Problem(bad, y, x0, scs.LogisticLoss(1 / 50), 1e-1)
