@@ -92,12 +92,15 @@ int scs_ctx_stream(scs_ctx* ctx, uint64_t* stream_out);
 int scs_problem_create(scs_ctx* ctx, const double* A_colmajor, int64_t n_local, int64_t m, int64_t lda,
                        const double* y, int loss_kind, double loss_param, int label_mode, scs_problem** out);
 /* The same from a compressed-sparse-column shard (Julia SparseMatrixCSC{Float64,Int64}: colptr (m+1), rowval, nzval;
- * index_base 1 for Julia, 0 for scipy).  Only the stored entries cross PCIe; the shard is expanded on the device into
- * the dense resident layout every kernel of this library works on (there is no sparse compute path: a matrix whose
- * dense form does not fit in HBM is SCS_OOM). */
+ * index_base 1 for Julia, 0 for scipy).  Only the stored entries cross PCIe.  storage: 1 = expand on the device into the
+ * dense resident layout (dense kernels: HBM-roofline passes, tensor-core Gram); 2 = keep the shard sparse (CSR + CSC
+ * copies; k_sp_forward / k_sp_adjoint / k_sp_gram, ~12 bytes per stored entry and pass; no int8 Gram, no GGN
+ * underdetermined branch, no scs_problem_read_rows); 0 = sparse when fewer than 4 % of the entries are stored.
+ * scs_problem_is_sparse reports which one was taken.  scs_get_gram_path returns 3 for the sparse Gram. */
 int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                            int64_t index_base, int64_t n_local, int64_t m, const double* y, int loss_kind,
-                           double loss_param, int label_mode, scs_problem** out);
+                           double loss_param, int label_mode, int storage, scs_problem** out);
+int scs_problem_is_sparse(scs_problem* p, int* sparse, int64_t* nnz);
 /* Synthetic shard generated on the device (bench / full-size invariants): rows [row0,row0+n_local) of the
  * n_total x m problem of oracle/synth.py (Philox-4x32-10, seed).  task: 0 = logistic labels, 1 = LS targets. */
 int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64_t row0, int64_t n_local, int64_t m,

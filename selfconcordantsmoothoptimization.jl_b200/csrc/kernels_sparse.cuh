@@ -1,0 +1,103 @@
+// K1s / K2s — streaming passes and Gram for a SPARSE shard (the README builds A with sprandn(n, m, 0.01),
+// README.md:105; ggn_score_step types J as possibly SparseMatrixCSC, prox-GGN-SCORE.jl:114).
+// The shard is resident twice: CSR (row pointers, 32-bit column indices, values) for the row-oriented forward pass and
+// CSC for the column-oriented adjoint and Gram.  Per stored entry a pass moves 12 bytes instead of 8 bytes per dense
+// element: at 1 % density a pass is ~66x less traffic than the dense kernels.
+//
+//   k_sp_forward : z_i = sum_p val_p x[col_p] per row (8 lanes per row), then the same loss_row as the dense pass.
+//   k_sp_adjoint : g_j = sum_p val_p r[row_p] per column (one warp per column, fixed shuffle tree).
+//   k_sp_gram    : column k of G = A' diag(w) A:  sum over the stored rows i of column k of (w_i a_ik) * (row i of A),
+//                  accumulated in a shared-memory vector of m doubles by ONE warp in a fixed order (row after row, lane
+//                  l takes the l-th, (l+32)-th ... entry of the row: distinct columns, so no two lanes ever touch the same
+//                  address) => deterministic without atomics.  The lower triangle is then mirrored.
+// All reductions use fixed trees: results are bit-reproducible.
+#pragma once
+#include "common.cuh"
+#include "kernels_stream.cuh"
+
+namespace scs {
+
+constexpr int kSpFwdThreads = 256;
+constexpr int kSpFwdRows = kSpFwdThreads / 8;  // rows per CTA
+
+__global__ void __launch_bounds__(kSpFwdThreads)
+k_sp_forward(const int64_t* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals, int64_t n,
+             int64_t row_lo, int64_t row_hi, const double* __restrict__ x, const double* __restrict__ y, LossParams lp,
+             double* __restrict__ z_out, double* __restrict__ r_out, double* __restrict__ w_out,
+             double* __restrict__ loss_part) {
+  __shared__ double red[32];
+  const int sub = threadIdx.x & 7;
+  const int64_t i = (int64_t)blockIdx.x * kSpFwdRows + (threadIdx.x >> 3);
+  double part = 0.0;
+  const bool valid = i < n;
+  double acc = 0.0;
+  if (valid) {
+    const int64_t p1 = rowptr[i + 1];
+    for (int64_t p = rowptr[i] + sub; p < p1; p += 8) acc = fma(vals[p], x[colidx[p]], acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // unconditional: every lane of the warp takes part
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (valid && sub == 0) {
+    double z = acc, t, r, w;
+    loss_row(lp, z, y[i], t, r, w);
+    if (i < row_lo || i >= row_hi) t = r = w = z = 0.0;  // rows of another mini-batch
+    if (lp.weight_kind == 2) {  // GGN parts (see k_forward)
+      z = t;
+      t = 0.0;
+    }
+    part = t;
+    if (z_out) z_out[i] = z;
+    if (r_out) r_out[i] = r;
+    if (w_out) w_out[i] = w;
+  }
+  const double tot = block_sum<kSpFwdThreads>(part, red);
+  if (threadIdx.x == 0) loss_part[blockIdx.x] = tot;
+}
+
+// g_j = sum over the stored entries of column j of val * r[row].  One warp per column; grid = ceil(m / 8) CTAs of 256.
+__global__ void __launch_bounds__(256)
+k_sp_adjoint(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ cvals, int m,
+             const double* __restrict__ r, double* __restrict__ g) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= m) return;
+  double a0 = 0.0, a1 = 0.0;
+  const int64_t p1 = colptr[j + 1];
+  int64_t p = colptr[j] + lane;
+  for (; p + 32 < p1; p += 64) {
+    a0 = fma(cvals[p], r[rowidx[p]], a0);
+    a1 = fma(cvals[p + 32], r[rowidx[p + 32]], a1);
+  }
+  if (p < p1) a0 = fma(cvals[p], r[rowidx[p]], a0);
+  const double s = warp_sum(a0 + a1);
+  if (lane == 0) g[j] = s;
+}
+
+// Column k of G (all m entries) into G[:, k]; one warp per CTA, dynamic shared memory = m doubles.
+__global__ void __launch_bounds__(32)
+k_sp_gram(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ cvals,
+          const int64_t* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+          const double* __restrict__ w, int m, double* __restrict__ G) {
+  extern __shared__ double acc[];
+  const int lane = threadIdx.x;
+  for (int k = blockIdx.x; k < m; k += gridDim.x) {
+    for (int j = lane; j < m; j += 32) acc[j] = 0.0;
+    __syncwarp();
+    const int64_t p1 = colptr[k + 1];
+    for (int64_t p = colptr[k]; p < p1; ++p) {
+      const int i = rowidx[p];
+      const double c = w[i] * cvals[p];
+      if (c != 0.0) {  // rows outside the active mini-batch carry w = 0
+        const int64_t q1 = rowptr[i + 1];
+        for (int64_t q = rowptr[i] + lane; q < q1; q += 32) acc[colidx[q]] = fma(c, vals[q], acc[colidx[q]]);
+      }
+      __syncwarp();
+    }
+    double* out = G + (int64_t)k * m;
+    for (int j = lane; j < m; j += 32) out[j] = acc[j];
+    __syncwarp();
+  }
+}
+
+}  // namespace scs

@@ -19,6 +19,7 @@
 #include "kernels_i8gram.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_sparse.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_vec.cuh"
 #include "nccl_dyn.hpp"
@@ -211,6 +212,12 @@ struct scs_problem {
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
   double* d_u = nullptr;  // row vector of the GGN wide branch (ldd doubles, allocated on first use)
+  // sparse shard (kernels_sparse.cuh): CSR + CSC copies, no dense A
+  bool sparse = false;
+  int64_t nnz = 0;
+  int64_t *d_rowptr = nullptr, *d_colptr = nullptr;
+  int *d_colidx = nullptr, *d_rowidx = nullptr;
+  double *d_vals = nullptr, *d_cvals = nullptr;
   // held-out data (model.Atest / model.ytest): a second resident shard whose loss is recorded next to every history
   // entry of scs_solve (ftest, iterate.jl:169-176; utils.jl:55-57)
   scs_problem* test = nullptr;
@@ -263,6 +270,14 @@ static int run_forward(scs_problem* p, const double* dx, int wk) {
   StageTimer t(c, ST_FWD);
   LossParams lp = p->loss;
   lp.weight_kind = wk;
+  if (p->sparse) {  // all rows, the mini-batch window is a mask
+    const int64_t blocks = (p->n + kSpFwdRows - 1) / kSpFwdRows;
+    LAUNCH(c, k_sp_forward, (unsigned)blocks, kSpFwdThreads, 0, (const int64_t*)p->d_rowptr, (const int*)p->d_colidx,
+           (const double*)p->d_vals, p->n, p->win_lo, p->win_hi, dx, (const double*)p->dy, lp, p->dz, p->dr, p->dw,
+           p->d_losspart);
+    LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_losspart, blocks, p->d_gl + p->m);
+    return SCS_OK;
+  }
   const int64_t nproc = p->ahi - p->alo;
   const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
   if (blocks > 0)
@@ -275,6 +290,11 @@ static int run_forward(scs_problem* p, const double* dx, int wk) {
 static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
   scs_ctx* c = p->ctx;
   StageTimer t(c, ST_ADJ);
+  if (p->sparse) {
+    LAUNCH(c, k_sp_adjoint, (unsigned)((p->m + 7) / 8), 256, 0, (const int64_t*)p->d_colptr, (const int*)p->d_rowidx,
+           (const double*)p->d_cvals, (int)p->m, dr, dout);
+    return SCS_OK;
+  }
   const int64_t nproc = p->ahi - p->alo;
   const int64_t blocks = (nproc + 64 * 8 - 1) / (64 * 8);
   if (blocks > 0)
@@ -329,7 +349,7 @@ static void fused_config(scs_problem* p, cudaLaunchConfig_t* cfg, cudaLaunchAttr
 
 // The shape decides the cluster geometry: CTA rank c owns columns [256c, 256c + 256); at most 16 CTAs per cluster.
 static bool fused_shape(const scs_problem* p, int* cluster) {
-  if (p->loss.kind == SCS_LOSS_QUADFORM) return false;
+  if (p->loss.kind == SCS_LOSS_QUADFORM || p->sparse) return false;
   if (p->ldd >= (int64_t)1 << 31) return false;  // TMA coordinates are 32-bit
   const int64_t cl = (p->m + kFuCols - 1) / kFuCols;
   if (cl > kFuMaxCluster) return false;
@@ -521,7 +541,7 @@ static int gram_setup(scs_problem* p) {
   const int nblk = (int)((m + kNB - 1) / kNB);
   SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16));  // 1/L_jj | inverted diagonal blocks | barrier
   CU_TRY(cudaMalloc((void**)&p->d_info, sizeof(int)));
-  if (p->loss.kind != SCS_LOSS_QUADFORM) {
+  if (p->loss.kind != SCS_LOSS_QUADFORM && !p->sparse) {
     GramPlan& pl = p->plan;
     pl.nt = (int)((m + kGT - 1) / kGT);
     pl.ntiles = pl.nt * (pl.nt + 1) / 2;
@@ -739,6 +759,30 @@ static int run_gram(scs_problem* p, XRef x) {
     LAUNCH(c, k_quadform_hess, dim3((m + 255) / 256, m), 256, 0, p->dA, p->ldd, m, p->d_G);
     return SCS_OK;
   }
+  if (p->sparse) {
+    p->last_gram_path = 3;
+    {
+      StageTimer t(c, ST_GRAM);
+      const size_t smem = (size_t)m * sizeof(double);
+      static size_t attr_smem = 0;
+      if (smem > attr_smem) {
+        if (smem > 220 * 1024) return fail(SCS_UNSUPPORTED, "sparse Gram: m > 28160 is not supported");
+        CU_TRY(cudaFuncSetAttribute(k_sp_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+      }
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
+      const int grid = std::min(m, c->num_sms * per_sm);
+      LAUNCH(c, k_sp_gram, grid, 32, smem, (const int64_t*)p->d_colptr, (const int*)p->d_rowidx, (const double*)p->d_cvals,
+             (const int64_t*)p->d_rowptr, (const int*)p->d_colidx, (const double*)p->d_vals, (const double*)p->dw, m,
+             p->d_G);
+    }
+    {
+      StageTimer t(c, ST_GRAMFIN);  // the two triangles were summed in different orders: keep the lower, mirror it
+      LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, p->d_G, (int64_t)m, m);
+    }
+    SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
+    return SCS_OK;
+  }
   bool want_i8 = p->gram_mode == 2 || (p->gram_mode == 0 && p->m >= 512 && p->win_hi - p->win_lo >= 32768);
   if (want_i8 && !p->i8_failed) {
     int done = 0;
@@ -847,6 +891,8 @@ static int run_ggn_wide(scs_problem* p, XRef x, double lam) {
   scs_ctx* c = p->ctx;
   if (c->world > 1)
     return fail(SCS_UNSUPPORTED, "ProxGGNSCORE underdetermined branch (n+1 <= m) needs all rows of the batch on one GPU");
+  if (p->sparse)
+    return fail(SCS_UNSUPPORTED, "ProxGGNSCORE underdetermined branch (n+1 <= m) is not implemented for a sparse shard");
   const int m = (int)p->m;
   const int nb = (int)(p->win_hi - p->win_lo);
   if (nb < 1) return fail(SCS_INVALID_ARG, "empty batch");
@@ -1006,7 +1052,7 @@ extern "C" int scs_get_stage_ms(scs_ctx* c, double* ms8, int64_t* calls8, int re
 // exported: problem lifetime
 // ------------------------------------------------------------------------------------------------
 static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind, double loss_param, int label_mode,
-                         scs_problem** out) {
+                         scs_problem** out, bool dense = true) {
   if (!ctx || !out) return fail(SCS_INVALID_ARG, "NULL argument");
   if (n_local < 1 || m < 1) return fail(SCS_INVALID_ARG, "n_local and m must be positive");
   if (m > 2000000000LL) return fail(SCS_INVALID_ARG, "m too large");
@@ -1028,7 +1074,8 @@ static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind
   p->loss.weight_kind = 0;
   p->loss.p = loss_param;
   *out = p;
-  SCS_TRY(dalloc(&p->dA, (size_t)p->ldd * m));
+  if (dense) SCS_TRY(dalloc(&p->dA, (size_t)p->ldd * m));
+  p->sparse = !dense;
   SCS_TRY(dalloc(&p->dy, p->ldd));
   SCS_TRY(dalloc(&p->dz, p->ldd));
   SCS_TRY(dalloc(&p->dr, p->ldd));
@@ -1041,7 +1088,7 @@ static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind
   for (auto v : vecs) SCS_TRY(dalloc(v, p->mp));
   SCS_TRY(dalloc(&p->d_scal, SC_COUNT));
   CU_TRY(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 8) * sizeof(double)));
-  p->fwd_blocks = (p->ldd + kFwdRows - 1) / kFwdRows;
+  p->fwd_blocks = dense ? (p->ldd + kFwdRows - 1) / kFwdRows : (n_local + kSpFwdRows - 1) / kSpFwdRows;
   p->win_lo = 0;
   p->win_hi = n_local;
   p->alo = 0;
@@ -1049,7 +1096,7 @@ static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind
   p->win_rows_global = 0;  // resolved (all-reduced) by the first set_window
   p->adj_blocks = (p->ldd + 64 * 8 - 1) / (64 * 8);
   SCS_TRY(dalloc(&p->d_losspart, p->fwd_blocks));
-  SCS_TRY(dalloc(&p->d_adjpart, (size_t)p->adj_blocks * m));
+  if (dense) SCS_TRY(dalloc(&p->d_adjpart, (size_t)p->adj_blocks * m));
   SCS_TRY(set_window(p, 0, n_local));  // whole shard; with several ranks this all-reduces the global row count
   return SCS_OK;
 }
@@ -1064,7 +1111,8 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u};
+                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
@@ -1100,16 +1148,27 @@ extern "C" int scs_problem_create(scs_ctx* ctx, const double* A, int64_t n_local
 
 extern "C" int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                                       int64_t index_base, int64_t n_local, int64_t m, const double* y, int loss_kind,
-                                      double loss_param, int label_mode, scs_problem** out) {
+                                      double loss_param, int label_mode, int storage, scs_problem** out) {
   if (!colptr || !y) return fail(SCS_INVALID_ARG, "colptr or y is NULL");
   if (index_base != 0 && index_base != 1) return fail(SCS_INVALID_ARG, "index_base must be 0 or 1");
-  if (m < 1) return fail(SCS_INVALID_ARG, "n_local and m must be positive");
+  if (storage < 0 || storage > 2) return fail(SCS_INVALID_ARG, "storage must be 0 (auto), 1 (dense) or 2 (sparse)");
+  if (m < 1 || n_local < 1) return fail(SCS_INVALID_ARG, "n_local and m must be positive");
   const int64_t nnz = colptr[m] - colptr[0];
   if (colptr[0] != index_base || nnz < 0) return fail(SCS_INVALID_ARG, "malformed colptr");
   for (int64_t j = 0; j < m; ++j)
     if (colptr[j + 1] < colptr[j]) return fail(SCS_INVALID_ARG, "colptr must be non-decreasing");
   if (nnz > 0 && (!rowval || !nzval)) return fail(SCS_INVALID_ARG, "rowval or nzval is NULL");
-  int s = problem_alloc(ctx, n_local, m, loss_kind, loss_param, label_mode, out);
+  for (int64_t p = 0; p < nnz; ++p) {
+    const int64_t i = rowval[p] - index_base;
+    if (i < 0 || i >= n_local) return fail(SCS_INVALID_ARG, "rowval entry outside 1..n_local");
+  }
+  // auto: the sparse kernels move 12 bytes per stored entry and gather x / r at random, the dense ones stream 8 bytes
+  // per element at the HBM roofline and have the tensor-core Gram: sparse pays off below a few percent density
+  const bool sparse = storage == 2 || (storage == 0 && (double)nnz < 0.04 * (double)n_local * (double)m && m <= 28160 &&
+                                       n_local < (1LL << 31) && loss_kind != SCS_LOSS_QUADFORM);
+  if (sparse && (m > 28160 || n_local >= (1LL << 31) || loss_kind == SCS_LOSS_QUADFORM))
+    return fail(SCS_UNSUPPORTED, "sparse storage needs m <= 28160, n_local < 2^31 and a row-separable loss");
+  int s = problem_alloc(ctx, n_local, m, loss_kind, loss_param, label_mode, out, !sparse);
   if (s != SCS_OK) {
     if (out && *out) {
       scs_problem_destroy(*out);
@@ -1118,34 +1177,80 @@ extern "C" int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const
     return s;
   }
   scs_problem* p = *out;
-  int64_t *d_cp = nullptr, *d_rv = nullptr;
-  double* d_nz = nullptr;
-  int* d_bad = nullptr;
-  int bad = 0;
-  cudaError_t e = cudaMalloc((void**)&d_cp, (m + 1) * sizeof(int64_t));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_rv, std::max<int64_t>(nnz, 1) * sizeof(int64_t));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_nz, std::max<int64_t>(nnz, 1) * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_cp, colptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_rv, rowval, nnz * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_nz, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->dy, y, n_local * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) {
-    k_scatter_csc<<<(unsigned)std::min<int64_t>(m, 4096), 256, 0, ctx->stream>>>(d_cp, d_rv, d_nz, index_base, n_local, (int)m,
-                                                                              p->ldd, p->dA, d_bad);
-    ctx->launches += 1;
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  dfree(d_cp), dfree(d_rv), dfree(d_nz), dfree(d_bad);
-  if (e != cudaSuccess || bad) {
+  auto bail = [&](cudaError_t e, const char* what) {
     scs_problem_destroy(p);
     *out = nullptr;
-    if (bad) return fail(SCS_INVALID_ARG, "rowval entry outside 1..n_local");
-    return fail(e == cudaErrorMemoryAllocation ? SCS_OOM : SCS_CUDA_ERROR, std::string("CSC upload failed: ") + cudaGetErrorString(e));
+    return fail(e == cudaErrorMemoryAllocation ? SCS_OOM : SCS_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t e = cudaMemcpyAsync(p->dy, y, n_local * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return bail(e, "upload of y failed");
+  // zero-based CSC on the host (32-bit row indices), then CSR by a counting pass (columns ascend inside every row)
+  std::vector<int64_t> cp(m + 1);
+  for (int64_t j = 0; j <= m; ++j) cp[j] = colptr[j] - index_base;
+  if (!sparse) {
+    int64_t *d_cp = nullptr, *d_rv = nullptr;
+    double* d_nz = nullptr;
+    int* d_bad = nullptr;
+    e = cudaMalloc((void**)&d_cp, (m + 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_rv, std::max<int64_t>(nnz, 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_nz, std::max<int64_t>(nnz, 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cp, colptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_rv, rowval, nnz * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_nz, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      k_scatter_csc<<<(unsigned)std::min<int64_t>(m, 4096), 256, 0, ctx->stream>>>(d_cp, d_rv, d_nz, index_base, n_local,
+                                                                                (int)m, p->ldd, p->dA, d_bad);
+      ctx->launches += 1;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dfree(d_cp), dfree(d_rv), dfree(d_nz), dfree(d_bad);
+    if (e != cudaSuccess) return bail(e, "CSC upload failed");
+    return SCS_OK;
   }
+  p->nnz = nnz;
+  std::vector<int> ri(std::max<int64_t>(nnz, 1)), ci(std::max<int64_t>(nnz, 1));
+  std::vector<int64_t> rp(n_local + 1, 0);
+  std::vector<double> rv(std::max<int64_t>(nnz, 1));
+  for (int64_t q = 0; q < nnz; ++q) {
+    ri[q] = (int)(rowval[q] - index_base);
+    rp[ri[q] + 1] += 1;
+  }
+  for (int64_t i = 0; i < n_local; ++i) rp[i + 1] += rp[i];
+  {
+    std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+    for (int64_t j = 0; j < m; ++j)
+      for (int64_t q = cp[j]; q < cp[j + 1]; ++q) {
+        const int64_t dst = fill[ri[q]]++;
+        ci[dst] = (int)j;
+        rv[dst] = nzval[q];
+      }
+  }
+  const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+  e = cudaMalloc((void**)&p->d_colptr, (m + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_rowptr, (n_local + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_rowidx, nz * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_colidx, nz * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_cvals, nz * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_vals, nz * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_colptr, cp.data(), (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rowptr, rp.data(), (n_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && nnz > 0) {
+    e = cudaMemcpyAsync(p->d_rowidx, ri.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_colidx, ci.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_cvals, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_vals, rv.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return bail(e, "sparse upload failed");
+  return SCS_OK;
+}
+extern "C" int scs_problem_is_sparse(scs_problem* p, int* sparse, int64_t* nnz) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (sparse) *sparse = p->sparse ? 1 : 0;
+  if (nnz) *nnz = p->nnz;
   return SCS_OK;
 }
 
@@ -1182,6 +1287,7 @@ extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64
 extern "C" int scs_problem_read_rows(scs_problem* p, int64_t row0, int64_t nrows, double* A_out, double* y_out) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   if (row0 < 0 || nrows < 0 || row0 + nrows > p->n) return fail(SCS_INVALID_ARG, "row range outside the shard");
+  if (p->sparse) return fail(SCS_UNSUPPORTED, "scs_problem_read_rows: the shard is resident in sparse form");
   CU_TRY(cudaSetDevice(p->ctx->device));
   CU_TRY(cudaStreamSynchronize(p->ctx->stream));
   if (A_out && nrows > 0)

@@ -89,8 +89,8 @@ function GPUProblem(ctx::GPUContext, model)
         S = SparseMatrixCSC{Float64,Int64}(model.A)
         colptr, rowval, nzval = S.colptr, S.rowval, S.nzval
         GC.@preserve colptr rowval nzval y check(ccall((:scs_problem_create_csc, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint,
-             Ref{Ptr{Cvoid}}), ctx.h, colptr, rowval, nzval, 1, n, m, y, code, param, lmode, out))
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint, Float64, Cint, Cint,
+             Ref{Ptr{Cvoid}}), ctx.h, colptr, rowval, nzval, 1, n, m, y, code, param, lmode, 0, out))  # storage 0 = auto
     else
         A = Matrix{Float64}(model.A)
         GC.@preserve A y check(ccall((:scs_problem_create, LIB), Cint,

@@ -162,7 +162,8 @@ class Problem:
     """
 
     def __init__(self, A, y, x0, f, lam, *, L=None, sol=None, C_set=None, P=None, out_fn=None, grad_fx=None,
-                 hess_fx=None, jac_yx=None, grad_fy=None, hess_fy=None, Atest=None, ytest=None, name=None, ctx=None):
+                 hess_fx=None, jac_yx=None, grad_fy=None, hess_fy=None, Atest=None, ytest=None, name=None, ctx=None,
+                 storage="auto"):
         if not isinstance(f, _BUILTIN):
             raise UnsupportedError(K.SCS_UNSUPPORTED,
                                    "arbitrary user f (ForwardDiff-only path) is not supported on the GPU: pass "
@@ -177,9 +178,11 @@ class Problem:
         self._h = C.c_void_p()
         self._reg_name = None
         self._host = None  # (A, y) as given: needed again only if iterate!(shuffle_batch=true) reorders the rows
+        self._storage = storage
         if A is not None and hasattr(A, "tocsc"):  # scipy.sparse (the README builds A with sprandn): CSC over the wire
             Ac = A.tocsc().astype(np.float64)
             Ac.sum_duplicates()
+            Ac.sort_indices()
             yv = K.vec(y, Ac.shape[0])
             if Ac.shape[1] != self.x0.shape[0]:
                 raise ValueError("x0 length must equal the number of columns of A")
@@ -189,7 +192,8 @@ class Problem:
             nz = np.ascontiguousarray(Ac.data, dtype=np.float64)
             self._host = (Ac, yv)
             K.check(K.lib().scs_problem_create_csc(self.ctx._h, K.iptr(cp), K.iptr(rv), K.dptr(nz), 0, self.n, self.m,
-                                                   K.dptr(yv), f.kind, f.param(), f.label_code(), C.byref(self._h)))
+                                                   K.dptr(yv), f.kind, f.param(), f.label_code(),
+                                                   {"auto": 0, "dense": 1, "sparse": 2}[storage], C.byref(self._h)))
             A = None
         if A is not None:
             A = np.asarray(A, dtype=np.float64)
@@ -224,16 +228,26 @@ class Problem:
                                                       "problem from host arrays or pass shuffle_batch=False")
         A, yv = self._host
         order = np.asarray(order, dtype=np.int64)
-        if hasattr(A, "tocsc"):
-            A = A.toarray()
-        A2 = np.asfortranarray(A[order])
         y2 = np.ascontiguousarray(yv[order])
         K.lib().scs_problem_destroy(self._h)
         self._h = C.c_void_p()
-        self._host = (A2, y2)
         self._reg_name = None
-        K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A2), self.n, self.m, A2.shape[0], K.dptr(y2),
-                                           self.f.kind, self.f.param(), self.f.label_code(), C.byref(self._h)))
+        if hasattr(A, "tocsc"):  # sparse shard: permute the rows of the CSC structure, same storage choice
+            A2 = A.tocsr()[order].tocsc()
+            A2.sort_indices()
+            cp = np.ascontiguousarray(A2.indptr, dtype=np.int64)
+            rv = np.ascontiguousarray(A2.indices, dtype=np.int64)
+            nz = np.ascontiguousarray(A2.data, dtype=np.float64)
+            self._host = (A2, y2)
+            K.check(K.lib().scs_problem_create_csc(self.ctx._h, K.iptr(cp), K.iptr(rv), K.dptr(nz), 0, self.n, self.m,
+                                                   K.dptr(y2), self.f.kind, self.f.param(), self.f.label_code(),
+                                                   {"auto": 0, "dense": 1, "sparse": 2}[self._storage],
+                                                   C.byref(self._h)))
+        else:
+            A2 = np.asfortranarray(A[order])
+            self._host = (A2, y2)
+            K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A2), self.n, self.m, A2.shape[0], K.dptr(y2),
+                                               self.f.kind, self.f.param(), self.f.label_code(), C.byref(self._h)))
         for name, val in getattr(self, "_modes", {}).items():  # kernel selections survive the rebuild
             getattr(self, name)(val)
 
@@ -368,7 +382,13 @@ class Problem:
     def gram_path(self):
         v = C.c_int()
         K.check(K.lib().scs_get_gram_path(self._h, C.byref(v)))
-        return {0: None, 1: "dmma", 2: "i8"}[v.value]
+        return {0: None, 1: "dmma", 2: "i8", 3: "sparse"}[v.value]
+
+    def is_sparse(self):
+        """(resident in sparse form?, stored entries)"""
+        a, b = C.c_int(), C.c_int64()
+        K.check(K.lib().scs_problem_is_sparse(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), b.value
 
     def set_gram_bits(self, bits):
         """Fixed-point bits kept below each column's largest entry by the emulated-fp64 Gram (24..50, default 40)."""

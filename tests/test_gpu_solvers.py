@@ -215,9 +215,24 @@ def test_ggn_wide_branch(scs, n, m, loss, ss_type):
         pg.close()
 
 
+def _sparse_problem(n, m, density, seed, loss="logistic"):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    A = sp.random(n, m, density=density, format="csc", random_state=rng, data_rvs=rng.standard_normal)
+    A = A + sp.csc_matrix((np.full(m, 0.3), (rng.integers(0, n, m), np.arange(m))), shape=(n, m))  # no empty column
+    Ad = A.toarray()
+    xt = np.where(rng.random(m) < 0.3, rng.standard_normal(m) * 2, 0.0)
+    if loss == "ls":
+        y = Ad @ xt + 0.1 * rng.standard_normal(n)
+    else:
+        y = np.where(rng.random(n) < 1 / (1 + np.exp(-(Ad @ xt))), 1.0, -1.0)
+    return sp.csc_matrix(A), Ad, y, rng.standard_normal(m) * 0.3
+
+
 def test_sparse_csc_input(scs):
-    """README.md:100-125: A = sprandn(n, m, 0.01).  A scipy CSC matrix goes over the wire as colptr / rowval / nzval
-    (scs_problem_create_csc) and must give exactly what the dense upload gives."""
+    """README.md:100-125: A = sprandn(n, m, 0.01).  A scipy CSC / CSR matrix goes over the wire as colptr / rowval /
+    nzval (scs_problem_create_csc); expanded on the device (storage="dense") it must give bit for bit what the dense
+    upload gives, kept sparse (storage="sparse": k_sp_forward / k_sp_adjoint / k_sp_gram) the same 1e-10 bar holds."""
     import scipy.sparse as sp
     A, y, x0 = cases.data("c1_readme_logreg_n")  # 1 %-dense look-alike of the README example
     rng = np.random.default_rng(3)
@@ -225,16 +240,75 @@ def test_sparse_csc_input(scs):
     so = O.iterate(O.ProxNSCORE(), O.Problem(A, y, x0, O.LogisticLoss(1 / 50), 1e-1), "l1", O.PHuberSmootherL1L2(1.0),
                    max_epoch=30, x_tol=1e-6, f_tol=1e-6)
     sols = []
-    for mat in (A, sp.csc_matrix(A), sp.csr_matrix(A)):
-        p = scs.Problem(mat, y, x0, scs.LogisticLoss(1 / 50), 1e-1)
+    for mat, storage in ((A, "auto"), (sp.csc_matrix(A), "dense"), (sp.csr_matrix(A), "dense"), (sp.csc_matrix(A), "sparse")):
+        p = scs.Problem(mat, y, x0, scs.LogisticLoss(1 / 50), 1e-1, storage=storage)
+        assert p.is_sparse()[0] == (storage == "sparse")
         sols.append(scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=30, x_tol=1e-6,
                                 f_tol=1e-6, verbose=0))
         p.close()
     for sg in sols:
         assert sg.epochs == so.epochs and relerr(sg.x, so.x) <= TOL and hist_err(sg.obj, so.obj) <= TOL
+        assert np.array_equal(sg.x != 0, so.x != 0)
     assert np.array_equal(sols[0].x, sols[1].x) and np.array_equal(sols[0].x, sols[2].x)  # same resident matrix
     with pytest.raises(scs.ScsError):  # malformed structure is an argument error, not a crash
         bad = sp.csc_matrix(A)
         bad.indices = bad.indices.copy()
         bad.indices[0] = A.shape[0] + 7
         scs.Problem(bad, y, x0, scs.LogisticLoss(1 / 50), 1e-1)
+
+
+@pytest.mark.parametrize("method,reg,loss", [("ProxNSCORE", "l1", "logistic"), ("ProxGGNSCORE", "l1", "consistent"),
+                                             ("ProxLQNSCORE", "l2", "logistic"), ("ProxGGNSCORE", "indbox", "ls")])
+@pytest.mark.parametrize("batch_size", [None, 1300])
+def test_sparse_compute_path(scs, method, reg, loss, batch_size):
+    """The shard stays sparse on the device (1 % density): every pass and the Gram run on the CSR / CSC copies; full
+    batch and mini-batches, host loop and in-library loop, against the oracle on the densified matrix."""
+    n, m = 6000, 400
+    As, Ad, y, x0 = _sparse_problem(n, m, 0.01, seed=21, loss="ls" if loss == "ls" else "logistic")
+    if loss == "ls":
+        Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
+    else:
+        mode = "consistent" if loss == "consistent" else "literal"
+        Lo, Lg = O.LogisticLoss(1 / n, mode), scs.LogisticLoss(1 / n, mode)
+    kwp = dict(C_set=(-0.5, 0.5)) if reg == "indbox" else {}
+    ho = O.PHuberSmootherIndBox(-0.5, 0.5, 0.6) if reg == "indbox" else O.PHuberSmootherL1L2(1.0)
+    kw = dict(max_epoch=6, alpha=0.9, batch_size=batch_size)
+    so = O.iterate(getattr(O, method)(), O.Problem(Ad, y, x0, Lo, 1e-3, **kwp), reg, ho, **kw)
+    for device_loop in (False, True):
+        pg = scs.Problem(As, y, x0, Lg, 1e-3, storage="sparse", **kwp)
+        assert pg.is_sparse() == (True, As.nnz)
+        hg = scs.PHuberSmootherIndBox(-0.5, 0.5, 0.6) if reg == "indbox" else scs.PHuberSmootherL1L2(1.0)
+        sg = scs.iterate(getattr(scs, method)(), pg, reg, hg, verbose=0, device_loop=device_loop, shuffle_batch=False, **kw)
+        assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj)
+        assert relerr(sg.x, so.x) <= TOL, relerr(sg.x, so.x)
+        assert hist_err(sg.obj, so.obj) <= TOL
+        if method != "ProxLQNSCORE":
+            assert pg.gram_path() == "sparse"
+        pg.close()
+
+
+def test_sparse_components_and_auto_storage(scs):
+    import scipy.sparse as sp
+    n, m = 3001, 257
+    As, Ad, y, x = _sparse_problem(n, m, 0.02, seed=5)
+    p = scs.Problem(As, y, x, scs.LogisticLoss(1 / n, "consistent"), 0.1)  # 2 % stored: auto keeps it sparse
+    assert p.is_sparse()[0]
+    Lo = O.LogisticLoss(1 / n, "consistent")
+    z = Ad @ x
+    for wk in ("newton", "ggn"):
+        fv, g, zg, rg, wg = p.loss_eval(x, weights=wk, want_rows=True)
+        r, w = (Lo.grad_weights(z, y), Lo.hess_weights(z, y)) if wk == "newton" else Lo.ggn_weights(z, y)
+        assert relerr(zg, z) <= 1e-13 and abs(fv - Lo.f(Ad, y, x)) <= 1e-13 * abs(Lo.f(Ad, y, x))
+        np.testing.assert_allclose(rg, r, rtol=1e-11, atol=1e-300)
+        assert relerr(g, Ad.T @ r) <= 1e-12
+        G = p.gram(x, weights=wk)
+        Gref = Ad.T @ (w[:, None] * Ad)
+        assert np.array_equal(G, G.T)
+        d = np.sqrt(np.diag(Gref))
+        assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 1e-13
+        assert np.array_equal(G, p.gram(x, weights=wk))  # bit-reproducible
+    p.close()
+    dense_ish = sp.csc_matrix(np.where(np.random.default_rng(1).random((300, 40)) < 0.5, 1.0, 0.0))
+    q = scs.Problem(dense_ish, np.ones(300), np.zeros(40), scs.LeastSquaresLoss(300.0), 0.1)  # 50 % stored: expanded
+    assert not q.is_sparse()[0]
+    q.close()
