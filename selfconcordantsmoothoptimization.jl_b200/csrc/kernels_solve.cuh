@@ -193,8 +193,11 @@ SCS_DEVINL void load_tile_T(double* dst, const double* __restrict__ M, int64_t l
 
 // Trailing update A22 -= L21 * L21'  (lower 64x64 tiles only) on CTAs [0, ntiles); CTAs >= ntiles update the
 // right-hand side below the block: b_i -= sum_c L[i, k0+c] y_c (128 rows each).  128 threads.
+// tile0: first triangular tile index handled by CTA 0 (the look-ahead sequence passes 1: the diagonal tile right below
+// the panel belongs to k_chol_diag).
 __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0, int ntiles,
-                                                     double* __restrict__ bvec, const double* __restrict__ yvec) {
+                                                     double* __restrict__ bvec, const double* __restrict__ yvec,
+                                                     int tile0) {
   extern __shared__ double tile_sh[];
   double* As = tile_sh;
   double* Bs = tile_sh + kNB * kTS;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
   }
   int ti, tj;
   {
-    const int tt = blockIdx.x;
+    const int tt = blockIdx.x + tile0;
     int r = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
     while ((r + 1) * (r + 2) / 2 <= tt) ++r;
     while (r * (r + 1) / 2 > tt) --r;
@@ -262,6 +265,239 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
         const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
         if (row < m && col < m && row >= col) M[(int64_t)col * ld + row] = old[i][j][h] - acc[i][j][h];
       }
+}
+
+// ---- look-ahead sequence (default): k_chol_diag -> k_chol_trsm on the main stream, k_syrk_update on a second one ------
+// The per-step chain of the right-looking factorisation is  factor L_kk -> L21 = A21 L_kk^-T -> update of the next
+// diagonal tile -> factor L_(k+1)(k+1).  Everything else (the rest of the trailing update) is off that chain, so it runs
+// on a second stream while the next diagonal block is being factored:
+//   k_chol_diag(k)  : ONE CTA.  D = A_kk - L_(k,k-1) L_(k,k-1)' (the previous panel's update of this tile, DMMA), then
+//                     a two-level factorisation of the 64x64 tile: four 16-column panels; a panel is factored by ONE
+//                     warp entirely in registers (lane l owns rows l and l+32 of the panel, pivots and multipliers move
+//                     by warp shuffles: no barrier and no shared-memory round trip on the per-column chain), the rank-16
+//                     update of the rest of the tile is 8x8x4 DMMAs spread over all warps.  The right-hand side is a
+//                     65th row of the tile, so y_k = L_kk^-1 b_k falls out of the same sweep.
+//   k_chol_trsm(k)  : X L_kk' = A21 by substitution, one thread per row with the 64 entries of the row in registers
+//                     (L_kk broadcast from shared memory), and b_i -= L21[i,:] y_k for the rows below.
+//   k_syrk_update(k): A22 -= L21 L21' for all lower tiles except the first diagonal one (tile0 = 1).
+constexpr int kCholDiagThreads = 256;
+constexpr int kCholDiagSmem = (kNB * kLS + kNB * kTS + 4 * kNB) * 8;
+#define SCS_STAMP(i)                                     \
+  do {                                                   \
+    if (prof != nullptr && tid == 0) prof[i] = clock64(); \
+  } while (0)
+__global__ void __launch_bounds__(kCholDiagThreads)
+k_chol_diag(double* __restrict__ M, int64_t ld, int m, int k0, double* __restrict__ rdiag_g, int* __restrict__ info,
+            const double* __restrict__ bvec, double* __restrict__ yvec, long long* __restrict__ prof) {
+  extern __shared__ double dsh[];
+  double* D = dsh;                 // the tile, D[r][c] (row stride kLS); the factor on exit
+  double* As = D + kNB * kLS;      // phase 0: As[p][i] = L[k0+i, k0-64+p]; phase 1: Ps[k][r] = panel column k, row r
+  double* rds = As + kNB * kTS;    // 1 / L_jj
+  double* bk = rds + kNB;          // right-hand side of this block, updated panel by panel
+  double* ys = bk + kNB;           // y_k
+  const int nb = min(kNB, m - k0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  SCS_STAMP(0);
+  // ---- phase 0: this tile with the previous panel's update applied (identity padding past nb).  One round trip:
+  // every thread has its 16 entries of the tile and its 16 entries of the panel rows in flight before the first store.
+  {
+    const int i = tid & 63, pq = tid >> 6;
+    double vd[16], va[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = pq + 4 * u;
+      vd[u] = (i < nb && c <= i) ? M[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
+      va[u] = (k0 > 0 && i < nb) ? M[(int64_t)(k0 - kNB + c) * ld + k0 + i] : 0.0;
+    }
+    if (tid >= 192) bk[tid - 192] = (tid - 192) < nb ? bvec[k0 + tid - 192] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = pq + 4 * u;
+      D[i * kLS + c] = vd[u];
+      As[c * kTS + i] = va[u];
+    }
+  }
+  __syncthreads();
+  SCS_STAMP(1);
+  if (k0 > 0) {  // D -= L(k,k-1) L(k,k-1)': 4 warps x (32x32), 8 shared-memory loads per 16 DMMAs
+    if (tid < 128) {
+      const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+      double acc[4][4][2] = {};
+      tile_mma_64(As, As, wm, wn, g, t, acc);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = wm + 8 * i + g, col = wn + 8 * j + 2 * t + h;
+            if (col <= row) D[row * kLS + col] -= acc[i][j][h];  // rows past nb: As is zero there
+          }
+    }
+    __syncthreads();
+  }
+  SCS_STAMP(2);
+  // ---- phase 1: four 16-column panels
+#pragma unroll 1
+  for (int c0 = 0; c0 < kNB; c0 += 16) {
+    if (warp == 0) {
+      const int rA = c0 + lane, rB = c0 + lane + 32;
+      double a[16], b2[16], e[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        a[k] = rA < kNB ? D[rA * kLS + c0 + k] : 0.0;
+        b2[k] = rB < kNB ? D[rB * kLS + c0 + k] : 0.0;
+        e[k] = bk[c0 + k];
+      }
+      double piv = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (lane == 0 && c0 + j < nb && !(piv > 0.0) && info[0] == 0) info[0] = k0 + c0 + j + 1;
+        const double rd = rsqrt(piv);
+        const double la = lane > j ? a[j] * rd : (lane == j ? piv * rd : 0.0);
+        const double lb = b2[j] * rd, le = e[j] * rd;
+        a[j] = la;
+        b2[j] = lb;
+        e[j] = le;
+        if (lane == j) rds[c0 + j] = rd;
+        if (j + 1 < 16) {
+          // the next pivot first, from lane j+1's own multiplier (no shuffle on the pivot chain); the general update
+          // below produces the same bits for that entry
+          piv = __shfl_sync(0xffffffffu, fma(-la, la, a[j + 1]), j + 1);
+        }
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) {
+          const double mlt = __shfl_sync(0xffffffffu, la, c);  // L[c0+c][c0+j]
+          a[c] = fma(-la, mlt, a[c]);
+          b2[c] = fma(-lb, mlt, b2[c]);
+          e[c] = fma(-le, mlt, e[c]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (rA < kNB) {
+          D[rA * kLS + c0 + k] = (c0 + k <= rA) ? a[k] : 0.0;
+          if (lane >= 16) As[k * kTS + rA] = a[k];
+        }
+        if (rB < kNB) {
+          D[rB * kLS + c0 + k] = b2[k];
+          As[k * kTS + rB] = b2[k];
+        }
+        if (lane == 0) ys[c0 + k] = e[k];
+      }
+    }
+    __syncthreads();
+    SCS_STAMP(3 + (c0 >> 3));
+    const int T0 = c0 + 16;
+    if (T0 < kNB) {
+      const int nt8 = (kNB - T0) >> 3, ntile = nt8 * (nt8 + 1) / 2;
+      for (int tix = warp; tix < ntile; tix += kCholDiagThreads / 32) {
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= tix) ++ti;
+        const int tj = tix - ti * (ti + 1) / 2;
+        const int r0 = T0 + 8 * ti, cc0 = T0 + 8 * tj;
+        double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx)
+          dmma_m8n8k4(u0, u1, As[(4 * sidx + t) * kTS + r0 + g], As[(4 * sidx + t) * kTS + cc0 + g]);
+        D[(r0 + g) * kLS + cc0 + 2 * t] -= u0;
+        D[(r0 + g) * kLS + cc0 + 2 * t + 1] -= u1;
+      }
+      if (tid >= 192 && T0 + (tid - 192) < kNB) {  // the right-hand-side row
+        const int c = T0 + (tid - 192);
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sacc = fma(ys[c0 + k], As[k * kTS + c], sacc);
+        bk[c] -= sacc;
+      }
+      __syncthreads();
+      SCS_STAMP(4 + (c0 >> 3));
+    }
+  }
+  // ---- phase 2: store L_kk, 1/L_jj and y_k
+  {
+    const int i = tid & 63, pq = tid >> 6;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = pq + 4 * u;
+      if (i < nb && c <= i) M[(int64_t)(k0 + c) * ld + k0 + i] = D[i * kLS + c];
+    }
+  }
+  if (tid < nb) {
+    rdiag_g[k0 + tid] = rds[tid];
+    yvec[k0 + tid] = ys[tid];
+  }
+  SCS_STAMP(10);
+}
+
+// X L_kk' = A21 for the 64 rows [k0 + 64 + 64*blockIdx.x, ...): thread = row (the first two warps; all eight warps stage
+// L_kk), right-looking over the columns with the 64 entries of the row in registers and L_kk broadcast from shared
+// memory (LDS.128: measured faster than the 4-threads-per-row shuffle layout of k_panel, 9.5k vs 15.5k cycles), and the
+// update of the right-hand side below the block.  Block k is full (there are rows below it).
+// kIdentity: the rows are those of the identity instead, for every diagonal block at once (k0 = 64*blockIdx.x), and
+// X = L_kk^-T is stored as Wt[blockIdx.x][r][c] — the layout k_bwd_all reads.
+constexpr int kTrsmThreads = 256;
+template <bool kIdentity>
+__global__ void __launch_bounds__(kTrsmThreads) k_chol_trsm(double* __restrict__ M, int64_t ld, int m, int k0_,
+                                                            const double* __restrict__ rdiag_g,
+                                                            double* __restrict__ bvec, const double* __restrict__ yvec,
+                                                            double* __restrict__ Wt_all, long long* __restrict__ prof) {
+  __shared__ __align__(16) double Lsm[kNB * kNB];  // Lsm[c][cp] = L[k0+cp][k0+c]
+  __shared__ double rds[kNB], ys[kNB];
+  const int tid = threadIdx.x;
+  const int k0 = kIdentity ? (int)blockIdx.x * kNB : k0_;
+  const int nb = min(kNB, m - k0);
+  const int row = k0 + kNB + (int)blockIdx.x * kNB + tid;
+  if (blockIdx.x != 0) prof = nullptr;
+  SCS_STAMP(0);
+  double x[kNB];
+  {
+    const int i = tid & 63, pq = tid >> 6;
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = pq + 4 * u;
+      v[u] = (i < nb && c < nb && i >= c) ? M[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
+    }
+    if (tid < kNB) {
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) {
+        if (kIdentity)
+          x[c] = c == tid ? 1.0 : 0.0;
+        else
+          x[c] = row < m ? M[(int64_t)(k0 + c) * ld + row] : 0.0;
+      }
+      rds[tid] = tid < nb ? rdiag_g[k0 + tid] : 1.0;
+      ys[tid] = (!kIdentity && tid < nb) ? yvec[k0 + tid] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) Lsm[(pq + 4 * u) * kNB + i] = v[u];
+  }
+  __syncthreads();
+  SCS_STAMP(1);
+  if (tid >= kNB) return;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int c = 0; c < kNB; ++c) {
+    x[c] *= rds[c];
+    if (c & 1)
+      s1 = fma(x[c], ys[c], s1);
+    else
+      s0 = fma(x[c], ys[c], s0);
+#pragma unroll
+    for (int cp = c + 1; cp < kNB; ++cp) x[cp] = fma(-x[c], Lsm[c * kNB + cp], x[cp]);
+  }
+  SCS_STAMP(2);
+  if (kIdentity) {
+    double* Wt = Wt_all + (int64_t)blockIdx.x * kNB * kNB;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) Wt[tid * kNB + c] = x[c];
+  } else if (row < m) {
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) M[(int64_t)(k0 + c) * ld + row] = x[c];
+    bvec[row] -= s0 + s1;
+  }
+  SCS_STAMP(3);
 }
 
 // ---- backward substitution  L' d = y  in two launches ----------------------------------------------------------
@@ -342,6 +578,69 @@ __global__ void __launch_bounds__(256) k_bwd_all(const double* __restrict__ M, i
       atomicAdd(bar, 1ULL);
     }
     want += gridDim.x;
+  }
+}
+
+// k_bwd_p2p: the same sweep with point-to-point dependencies instead of grid barriers.  CTA c owns column block c: it
+// keeps y_c in registers, subtracts L[block j, block c]' d_j for j = nblk-1 .. c+1 as soon as CTA j has published d_j
+// (one flag per block, release / acquire), then forms d_c = (L_cc^-1)' y_c and publishes it.  The only serial chain is
+// flag -> 64 doubles of d_j -> two 64x64 mat-vecs -> flag; the L blocks and Wt_c are prefetched before the wait.
+// All CTAs must be co-resident (cooperative launch, gridDim.x = nblk).
+__global__ void __launch_bounds__(256) k_bwd_p2p(const double* __restrict__ M, int64_t ld, int m,
+                                                 const double* __restrict__ Wt, const double* __restrict__ y,
+                                                 double* __restrict__ d, int* __restrict__ flags) {
+  __shared__ double dj[kNB], yk[kNB];
+  const int nblk = (m + kNB - 1) / kNB;
+  const int cblk = blockIdx.x, k0c = cblk * kNB, nbc = min(kNB, m - k0c);
+  const int tid = threadIdx.x, col = tid >> 2, q = tid & 3;
+  double w[16];
+  {
+    const double* wp = Wt + (int64_t)cblk * kNB * kNB + col * kNB + 16 * q;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = wp[i];
+  }
+  double yv = (q == 0 && col < nbc) ? y[k0c + col] : 0.0;
+  for (int j = nblk - 1; j > cblk; --j) {
+    const int k0j = j * kNB, nbj = min(kNB, m - k0j);
+    double lp[16];
+    {
+      const double* src = M + (int64_t)(k0c + col) * ld + k0j + 16 * q;  // col < nbc = 64 here (cblk is not the last block)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) lp[i] = (16 * q + i < nbj) ? src[i] : 0.0;
+    }
+    if (tid == 0) {
+      const long long t0 = clock64();
+      while (true) {
+        int seen;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + j) : "memory");
+        if (seen != 0) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __syncthreads();
+    if (tid < kNB) dj[tid] = tid < nbj ? __ldcg(d + k0j + tid) : 0.0;
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc = fma(lp[i], dj[16 * q + i], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) yv -= acc;
+  }
+  if (q == 0) yk[col] = yv;
+  __syncthreads();
+  {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc = fma(w[i], yk[16 * q + i], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0 && col < nbc) d[k0c + col] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + cblk), "r"(1) : "memory");
   }
 }
 
@@ -430,6 +729,17 @@ __global__ void k_wide_v(const double* __restrict__ gr, const double* __restrict
 }
 
 // ---- pivoted LU fallback (unblocked, right-looking) -------------------------------------------
+// The Cholesky sequence writes the lower triangle only.  When the caller's matrix is symmetric in storage (every Gram
+// this library forms is), the original is therefore still there: upper triangle + a saved diagonal.  No m x m copy.
+__global__ void k_save_diag(const double* __restrict__ M, int64_t ld, int m, double* __restrict__ diag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) diag[j] = M[(int64_t)j * ld + j];
+}
+__global__ void k_restore_lower(double* __restrict__ M, int64_t ld, int m, const double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i < m && i > j) M[(int64_t)j * ld + i] = M[(int64_t)i * ld + j];
+  if (i == j && i < m) M[(int64_t)j * ld + j] = diag[j];
+}
 // Fill the upper triangle from the lower one.
 __global__ void k_symmetrize(double* __restrict__ M, int64_t ld, int m) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;

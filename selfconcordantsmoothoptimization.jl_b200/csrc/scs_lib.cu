@@ -65,6 +65,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct scs_ctx {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // trailing updates of the look-ahead Cholesky (run_solve)
+  cudaEvent_t ev_trsm[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+  int solve_mode = 0;  // 0 = look-ahead sequence, 1 = k_panel / k_syrk_update sequence (SCS_SOLVE_LEGACY=1)
   NcclComm comm = nullptr;
   int num_sms = 148;
   int64_t launches = 0;
@@ -537,9 +540,9 @@ static int gram_setup(scs_problem* p) {
   scs_ctx* c = p->ctx;
   const int64_t m = p->m;
   SCS_TRY(dalloc(&p->d_G, (size_t)m * m));
-  SCS_TRY(dalloc(&p->d_Gsave, (size_t)m * m));
+  SCS_TRY(dalloc(&p->d_Gsave, round_up(m, 16)));  // the diagonal (run_solve, sym = true)
   const int nblk = (int)((m + kNB - 1) / kNB);
-  SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16));  // 1/L_jj | inverted diagonal blocks | barrier
+  SCS_TRY(dalloc(&p->d_Linv, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16 + nblk));  // 1/L_jj | inverted diagonal blocks | barrier
   CU_TRY(cudaMalloc((void**)&p->d_info, sizeof(int)));
   if (p->loss.kind != SCS_LOSS_QUADFORM && !p->sparse) {
     GramPlan& pl = p->plan;
@@ -811,12 +814,17 @@ static int run_gram(scs_problem* p, XRef x) {
   return SCS_OK;
 }
 
-// Solve M d = b on the device.  M (ld = m) is destroyed; Msave receives a copy first (for the LU fallback).
+// Solve M d = b on the device.  M (ld = m) is destroyed.  For the LU fallback the original must survive: sym = true
+// (M holds both triangles of a symmetric matrix): only the diagonal is saved (Msave: m doubles), the Cholesky never
+// writes the upper triangle; sym = false (only the lower triangle is trusted): Msave (m x m) receives a copy first.
 // b is destroyed; result in dsol.  tmp: m doubles.
 static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
-                     double* dsol, int m, int* used_fallback) {
+                     double* dsol, int m, int* used_fallback, bool sym) {
   StageTimer t(c, ST_SOLVE);
-  CU_TRY(cudaMemcpyAsync(Msave, M, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (sym)
+    LAUNCH(c, k_save_diag, (m + 255) / 256, 256, 0, (const double*)M, (int64_t)m, m, Msave);
+  else
+    CU_TRY(cudaMemcpyAsync(Msave, M, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   // the LU fallback needs the untouched right-hand side: keep it in dsol until the factorisation has succeeded
   CU_TRY(cudaMemcpyAsync(dsol, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
@@ -829,39 +837,109 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
       CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CU_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CU_TRY(cudaFuncSetAttribute(k_bwd_all, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDiagSmem));
+      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr_set = true;
     }
   }
   double* rdiag = Linv;  // first m doubles of the workspace hold 1/L_jj
-  // b rides along as an extra row of the factorisation: tmp receives y = L^-1 b block by block
-  for (int k = 0; k < nblk; ++k) {
-    const int k0 = k * kNB;
-    const int nb = std::min(kNB, m - k0);
-    const int rem = m - k0 - nb;
-    const int rb = (rem + kNB - 1) / kNB;
-    LAUNCH(c, k_panel, 2 + rb, 256, 0, M, (int64_t)m, m, k0, rdiag, d_info, b, tmp, rb);
-    if (rem > 0) {
-      const int ntiles = rb * (rb + 1) / 2;
-      LAUNCH(c, k_syrk_update, ntiles + (rem + 127) / 128, 128, kTileSmem, M, (int64_t)m, m, k0, ntiles, b,
-             (const double*)tmp);
+  double* Wt = Linv + round_up(m, 16);  // (L_kk^-1)' per diagonal block (k_invdiag below)
+  long long* d_prof = nullptr;  // SCS_CHOL_PROF=1: clock64 stamps of the second k_chol_diag launch go to stderr
+  static const bool chol_prof = getenv("SCS_CHOL_PROF") && atoi(getenv("SCS_CHOL_PROF"));
+  if (chol_prof && c->solve_mode == 0) {
+    CU_TRY(cudaMalloc((void**)&d_prof, 16 * sizeof(long long)));
+    CU_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), c->stream));
+  }
+  if (c->solve_mode == 0) {
+    // look-ahead sequence (kernels_solve.cuh): diag -> trsm on the main stream, the trailing update of step k on the
+    // second stream while diag(k+1) runs; trsm(k+1) waits for it.
+    bool upd_pending = false;
+    int upd_idx = 0;
+    for (int k = 0; k < nblk; ++k) {
+      const int k0 = k * kNB;
+      const int nb = std::min(kNB, m - k0);
+      const int rem = m - k0 - nb;
+      const int rb = (rem + kNB - 1) / kNB;
+      LAUNCH(c, k_chol_diag, 1, kCholDiagThreads, kCholDiagSmem, M, (int64_t)m, m, k0, rdiag, d_info, (const double*)b,
+             tmp, (k == 1 ? d_prof : (long long*)nullptr));
+      if (rem <= 0) break;
+      if (upd_pending) {
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_upd[upd_idx], 0));
+        upd_pending = false;
+      }
+      LAUNCH(c, k_chol_trsm<false>, rb, kTrsmThreads, 0, M, (int64_t)m, m, k0, (const double*)rdiag, b,
+             (const double*)tmp, (double*)nullptr, (k == 1 && d_prof ? d_prof + 11 : (long long*)nullptr));
+      const int ntiles = rb * (rb + 1) / 2 - 1;  // the first diagonal tile is k_chol_diag(k+1)'s
+      if (ntiles > 0) {
+        CU_TRY(cudaEventRecord(c->ev_trsm[k & 1], c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->stream2, c->ev_trsm[k & 1], 0));
+        k_syrk_update<<<ntiles, 128, kTileSmem, c->stream2>>>(M, (int64_t)m, m, k0, ntiles, b, (const double*)tmp, 1);
+        c->launches += 1;
+        CU_TRY(cudaGetLastError());
+        upd_idx = k & 1;
+        CU_TRY(cudaEventRecord(c->ev_upd[upd_idx], c->stream2));
+        upd_pending = true;
+      }
+    }
+    if (upd_pending) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_upd[upd_idx], 0));  // join (a later trsm normally has)
+  } else {
+    // b rides along as an extra row of the factorisation: tmp receives y = L^-1 b block by block
+    for (int k = 0; k < nblk; ++k) {
+      const int k0 = k * kNB;
+      const int nb = std::min(kNB, m - k0);
+      const int rem = m - k0 - nb;
+      const int rb = (rem + kNB - 1) / kNB;
+      LAUNCH(c, k_panel, 2 + rb, 256, 0, M, (int64_t)m, m, k0, rdiag, d_info, b, tmp, rb);
+      if (rem > 0) {
+        const int ntiles = rb * (rb + 1) / 2;
+        LAUNCH(c, k_syrk_update, ntiles + (rem + 127) / 128, 128, kTileSmem, M, (int64_t)m, m, k0, ntiles, b,
+               (const double*)tmp, 0);
+      }
     }
   }
   int info = 0;
   CU_TRY(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
+  if (d_prof) {
+    long long st[16];
+    CU_TRY(cudaMemcpy(st, d_prof, sizeof(st), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "k_chol_diag stamps (cycles from entry):");
+    for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", st[i] ? st[i] - st[0] : -1LL);
+    fprintf(stderr, "; k_chol_trsm: %lld %lld %lld\n", st[12] - st[11], st[13] - st[11], st[14] - st[11]);
+    cudaFree(d_prof);
+  }
   if (info == 0) {
     // tmp now holds y
     // backward substitution: invert the diagonal blocks (all at once), then one persistent kernel for the sweep
-    double* Wt = Linv + round_up(m, 16);
     unsigned long long* bar = (unsigned long long*)(Wt + (size_t)nblk * kNB * kNB);
-    LAUNCH(c, k_invdiag, nblk, 64, 0, (const double*)M, (int64_t)m, m, Wt);
-    CU_TRY(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), c->stream));
-    {
+    if (c->solve_mode == 0)
+      LAUNCH(c, k_chol_trsm<true>, nblk, kTrsmThreads, 0, M, (int64_t)m, m, 0, (const double*)rdiag, (double*)nullptr,
+             (const double*)nullptr, Wt, (long long*)nullptr);
+    else
+      LAUNCH(c, k_invdiag, nblk, 64, 0, (const double*)M, (int64_t)m, m, Wt);
+    int* flags = (int*)(bar + 2);
+    const double* Mc = M;
+    int64_t ldm = m;
+    int mm = m;
+    const double* Wc = Wt;
+    static int p2p_capacity = -1;  // co-resident CTAs of k_bwd_p2p on this device
+    if (p2p_capacity < 0) {
+      int per_sm = 0;
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bwd_p2p, 256, 0));
+      p2p_capacity = per_sm * c->num_sms;
+    }
+    if (c->solve_mode == 0 && nblk <= p2p_capacity) {
+      CU_TRY(cudaMemsetAsync(flags, 0, (size_t)nblk * sizeof(int), c->stream));
+      const double* yc = tmp;
+      void* args[] = {(void*)&Mc, (void*)&ldm, (void*)&mm, (void*)&Wc, (void*)&yc, (void*)&dsol, (void*)&flags};
+      cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_bwd_p2p, dim3(nblk), dim3(256), args, 0, c->stream);
+      c->launches += 1;
+      if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_bwd_p2p launch: ") + cudaGetErrorString(le));
+    } else {
+      CU_TRY(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), c->stream));
       int grid = std::min(c->num_sms, nblk);
-      const double* Mc = M;
-      int64_t ldm = m;
-      int mm = m;
-      const double* Wc = Wt;
       void* args[] = {(void*)&Mc, (void*)&ldm, (void*)&mm, (void*)&Wc, (void*)&tmp, (void*)&dsol, (void*)&bar};
       cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_bwd_all, dim3(grid), dim3(256), args, 0, c->stream);
       c->launches += 1;
@@ -873,7 +951,12 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   // not positive definite: partial-pivoting LU on the saved copy (symmetrised), still on the device
   *used_fallback = 1;
   CU_TRY(cudaMemcpyAsync(b, dsol, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, Msave, (int64_t)m, m);
+  if (sym) {
+    LAUNCH(c, k_restore_lower, dim3((m + 255) / 256, m), 256, 0, M, (int64_t)m, m, (const double*)Msave);
+    Msave = M;  // factor in place
+  } else {
+    LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, Msave, (int64_t)m, m);
+  }
   // restore b (the Cholesky path has not touched b yet, but keep the contract explicit)
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
   for (int k = 0; k < m; ++k) {
@@ -976,6 +1059,12 @@ extern "C" int scs_ctx_create(int device, int rank, int world, const void* id128
   c->world = world;
   c->num_sms = prop.multiProcessorCount;
   CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_trsm[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_upd[i], cudaEventDisableTiming));
+  }
+  if (const char* e = getenv("SCS_SOLVE_LEGACY")) c->solve_mode = atoi(e) ? 1 : 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -1011,6 +1100,11 @@ extern "C" int scs_ctx_destroy(scs_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_trsm[i]) cudaEventDestroy(c->ev_trsm[i]);
+    if (c->ev_upd[i]) cudaEventDestroy(c->ev_upd[i]);
+  }
   delete c;
   return SCS_OK;
 }
@@ -1711,7 +1805,7 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
         CU_TRY(cudaMemcpyAsync(p->d_q, p->d_rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       }
       SCS_TRY(run_solve(c, p->d_G, p->d_Gsave, p->d_Linv, p->d_info, p->d_q, p->d_t1, p->d_sol, m,
-                        &p->last_used_fallback));
+                        &p->last_used_fallback, true));
     }
     if (p->ss_type == 3) {
       const double* gqx = p->d_rhs;  // N: ∇q = grad_f + λgr
@@ -2017,7 +2111,7 @@ extern "C" int scs_linear_solve(scs_ctx* c, const double* M, const double* b, in
     dfree(dM), dfree(dS), dfree(dL), dfree(db), dfree(dt), dfree(dd), dfree(di);
   };
   if ((rc = dalloc(&dM, (size_t)m * m)) || (rc = dalloc(&dS, (size_t)m * m)) ||
-      (rc = dalloc(&dL, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16)) || (rc = dalloc(&db, m)) || (rc = dalloc(&dt, m)) ||
+      (rc = dalloc(&dL, (size_t)nblk * kNB * kNB + round_up(m, 16) + 16 + nblk)) || (rc = dalloc(&db, m)) || (rc = dalloc(&dt, m)) ||
       (rc = dalloc(&dd, m))) {
     cleanup();
     return rc;
@@ -2029,7 +2123,7 @@ extern "C" int scs_linear_solve(scs_ctx* c, const double* M, const double* b, in
   cudaMemcpyAsync(dM, M, (size_t)m * m * sizeof(double), cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(db, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, c->stream);
   int fb = 0;
-  rc = run_solve(c, dM, dS, dL, di, db, dt, dd, m, &fb);
+  rc = run_solve(c, dM, dS, dL, di, db, dt, dd, m, &fb, false);
   if (rc == SCS_OK) {
     cudaMemcpyAsync(d, dd, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     rc = ctx_sync(c);

@@ -120,7 +120,7 @@ def test_quadform_loss(scs):
     p.close()
 
 
-@pytest.mark.parametrize("m", [1, 2, 5, 63, 64, 65, 200, 777])
+@pytest.mark.parametrize("m", [1, 2, 5, 63, 64, 65, 128, 129, 200, 777, 1472])
 def test_linear_solve_spd_and_indefinite(scs, m):
     rng = np.random.default_rng(m)
     B = rng.standard_normal((m + 3, m))
