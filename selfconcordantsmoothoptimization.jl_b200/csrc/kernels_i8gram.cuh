@@ -3,9 +3,9 @@
 // fp64 has no tcgen05.mma kind, so  G = A' diag(w) A  (prox-GGN-SCORE.jl:129, prox-N-SCORE.jl:63) is evaluated
 // through exact integer arithmetic (Ozaki scheme II / CRT):
 //
-//   1. C = diag(sqrt(w)) A is brought to fixed point per column:  X_ij = rint(C_ij * 2^(b - e_j)),  |X| <= 2^b,
-//      2^e_j >= max_i |C_ij|  (bound: max sqrt(w) * colmax|A|).  Needs w >= 0 (Newton weights, consistent-label
-//      GGN weights, least squares); otherwise the caller stays on the DMMA kernel.
+//   1. C = diag(sqrt(w)) A is brought to fixed point per column:  X_ij = rint(C_ij * s_j),  s_j = T / (sqrt(wmax) ||A_j||_2),
+//      so ||X_j||_2 <= T for every column and |sum_i X_ij X_ik| <= T^2 (Cauchy-Schwarz).  Needs w >= 0 (Newton weights,
+//      consistent-label GGN weights, least squares); otherwise the caller stays on the DMMA kernel.
 //   2. k_residues writes, for each of the first nmod (10..15) pairwise-coprime moduli p_l <= 256, the symmetric residue plane
 //      x_l = X mod p_l as int8 (column-major, K = rows contiguous).
 //   3. k_i8syrk computes S_l = x_l' x_l mod p_l on lower-triangle 128x256 tiles with tcgen05.mma.kind::i8
@@ -13,12 +13,13 @@
 //      double-buffered), one K chunk (<= 65536 rows: |acc| <= 2^30) at a time; the epilogue warps pull the
 //      accumulator with tcgen05.ld, reduce mod p_l and store int8 partial residues.
 //   4. k_crt sums the chunk residues, reconstructs R = sum_i X_ij X_ik exactly by CRT in 128-bit integers
-//      (P = prod p_l > 2 n 2^(2b)) and writes G_jk = R * 2^(e_j + e_k - 2b) to both triangles.
+//      (P = prod p_l > 2 T^2) and writes G_jk = R / (s_j s_k) to both triangles.
 //
-// The only rounding is the fixed-point quantisation of C (b bits below the column maximum) and the final conversion
-// to fp64; the integer Gram itself is exact and bit-reproducible.  The host picks the shortest moduli prefix that
-// still gives b >= the requested bits (default 40: a quantisation error of 2^-40 (colmax/rms)/sqrt(n) relative to
-// the diagonal — below the rounding noise of an fp64 DGEMM of the same length; 13 moduli at n = 1e6, b = 48 needs 15).
+// The only rounding is the fixed-point quantisation of C and the final conversion to fp64; the integer Gram itself is
+// exact and bit-reproducible.  The quantisation error of an entry is ~0.4 / T of the diagonal scale whatever n is
+// (12 moduli: T = 2^46.9 -> 3e-15; 13: 2e-16, i.e. fp64 rounding level).  The host picks the shortest moduli prefix whose
+// T leaves every column at least the requested bits below its largest entry (default 38: 12 moduli for Gaussian-like
+// columns at n = 1e6), then uses all of that prefix's range.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -63,24 +64,37 @@ struct I8Plan {
 };
 
 // ---- column / row statistics -------------------------------------------------------------------------------
-// colmax[j] = max_i |A_ij|  (one pass over A, once per problem)
+// colmax[j] = max_i |A_ij|, colnorm2[j] = sum_i A_ij^2  (one pass over A, once per problem; fixed reduction tree)
 __global__ void __launch_bounds__(256) k_colabsmax(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
-                                                   double* __restrict__ colmax) {
-  __shared__ double red[32];
+                                                   double* __restrict__ colmax, double* __restrict__ colnorm2) {
+  __shared__ double red[32], red2[32];
   const int j = blockIdx.x;
   const double* col = A + (int64_t)j * ldd;
-  double v = 0.0;
+  double v = 0.0, s2 = 0.0;
   for (int64_t i = threadIdx.x * 2; i < n; i += 512) {
     const double2 a = ldg_stream2(col + i);
-    v = fmax(v, fmax(fabs(a.x), i + 1 < n ? fabs(a.y) : 0.0));
+    const double ay = i + 1 < n ? a.y : 0.0;
+    v = fmax(v, fmax(fabs(a.x), fabs(ay)));
+    s2 = fma(a.x, a.x, s2);
+    s2 = fma(ay, ay, s2);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  for (int o = 16; o > 0; o >>= 1) {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = v;
+    red2[threadIdx.x >> 5] = s2;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) v = fmax(v, red[q]);
+    for (int q = 1; q < 8; ++q) {
+      v = fmax(v, red[q]);
+      s2 += red2[q];
+    }
     colmax[j] = v;
+    colnorm2[j] = s2;
   }
 }
 // stat[0] = max_i w_i, stat[1] = min_i w_i   (single CTA)
@@ -113,21 +127,17 @@ __global__ void __launch_bounds__(kVecThreads) k_wstat(const double* __restrict_
     stat[1] = mn;
   }
 }
-// e_j: smallest integer with sqrt(wmax)*colmax_j <= 2^e_j;  scale_j = 2^(b - e_j)
-__global__ void k_colscale(const double* __restrict__ colmax, const double* __restrict__ stat, int m, int b,
-                           int* __restrict__ ecol, double* __restrict__ scale) {
+// Norm-equalised fixed point: scale_j = T / (sqrt(wmax) * ||A_j||_2), so that every column of X = rint(C scale) has
+// ||X_j||_2 <= T (C = diag(sqrt w) A, w <= wmax) and, by Cauchy-Schwarz, every entry of X'X is below T^2 < P/2: the CRT
+// range is spent on precision, not on the worst case n * max^2.  inv_j = 1 / scale_j undoes it after the CRT.
+__global__ void k_colscale(const double* __restrict__ colnorm2, const double* __restrict__ stat, int m, double T,
+                           double* __restrict__ inv, double* __restrict__ scale) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  const double bound = sqrt(fmax(stat[0], 0.0)) * colmax[j];
-  int e = 0;
-  if (bound > 0.0) {
-    const double f = frexp(bound, &e);  // bound = f * 2^e, f in [0.5, 1)
-    (void)f;
-  } else {
-    e = -1000;  // all-zero column: any scale works, X = 0
-  }
-  ecol[j] = e;
-  scale[j] = bound > 0.0 ? ldexp(1.0, b - e) : 0.0;
+  const double bound = sqrt(fmax(stat[0], 0.0)) * sqrt(colnorm2[j]);
+  const bool ok = bound > 0.0 && bound < 1e300;
+  scale[j] = ok ? T / bound : 0.0;  // all-zero column (or no weight): X = 0
+  inv[j] = ok ? bound / T : 0.0;
 }
 
 // ---- residue planes ------------------------------------------------------------------------------------------
@@ -738,10 +748,10 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
 
 // ---- CRT reconstruction -----------------------------------------------------------------------------------------
 // For each lower-triangle (jc >= kc): R = CRT({sum_c partial[l][c][jc][kc] mod p_l}) in (-P/2, P/2), then
-// G[jc,kc] = G[kc,jc] = R * 2^(e_jc + e_kc - 2b).  One thread reconstructs 4 consecutive kc (32-bit loads of the
+// G[jc,kc] = G[kc,jc] = R * inv_jc * inv_kc.  One thread reconstructs 4 consecutive kc (32-bit loads of the
 // int8 partial residues).
 __global__ void __launch_bounds__(256)
-k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ ecol, int b, double* __restrict__ G) {
+k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ inv, double* __restrict__ G) {
   const int kc0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
   const int jc = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (jc >= pl.m || kc0 >= pl.m || kc0 > jc) return;
@@ -773,7 +783,7 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ eco
     }
   }
   const unsigned __int128 P = ((unsigned __int128)c_P_hi[var] << 64) | c_P_lo[var];
-  const int ej = ecol[jc];
+  const double ij = inv[jc];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int kc = kc0 + e;
@@ -788,8 +798,7 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const int* __restrict__ eco
     const unsigned __int128 mag = neg ? (unsigned __int128)(-r) : (unsigned __int128)r;
     double d = ldexp((double)(unsigned long long)(mag >> 64), 64) + (double)(unsigned long long)mag;
     if (neg) d = -d;
-    const int ek = ecol[kc];
-    const double g = (ej < -900 || ek < -900) ? 0.0 : ldexp(d, ej + ek - 2 * b);
+    const double g = (d * ij) * inv[kc];
     G[(int64_t)kc * pl.m + jc] = g;
     G[(int64_t)jc * pl.m + kc] = g;
   }

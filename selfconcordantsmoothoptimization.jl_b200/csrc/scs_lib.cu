@@ -68,6 +68,9 @@ struct scs_ctx {
   cudaStream_t stream2 = nullptr;  // trailing updates of the look-ahead Cholesky (run_solve)
   cudaEvent_t ev_trsm[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
   int solve_mode = 0;  // 0 = look-ahead sequence, 1 = k_panel / k_syrk_update sequence (SCS_SOLVE_LEGACY=1)
+  bool solve_attr_set = false;
+  int p2p_capacity = -1;
+  size_t sp_gram_smem = 0;
   NcclComm comm = nullptr;
   int num_sms = 148;
   int64_t launches = 0;
@@ -200,11 +203,12 @@ struct scs_problem {
   bool i8_ready = false, i8_failed = false, i8_planes_valid = false;
   int8_t *d_planes = nullptr, *d_i8partial = nullptr;
   double *d_colmax = nullptr, *d_wstat = nullptr, *d_colscale = nullptr;
-  int* d_ecol = nullptr;
+  double *d_colinv = nullptr, *d_colnorm2 = nullptr;
+  double i8_T = 0.0;  // column 2-norm target of the fixed-point image (run_gram_i8)
   int2* d_i8tiles = nullptr;
   unsigned long long* d_i8progress = nullptr;
   int64_t ldx = 0;
-  int i8_b = 0, i8_clusters = 0, i8_bits = 40, i8_nmod = 0;
+  int i8_b = 0, i8_clusters = 0, i8_bits = 46, i8_nmod = 0;
   I8Plan i8plan{};
   CUtensorMap xmap{}, xmap_b{};
   // single-pass fused gradient (kernels_fused.cuh)
@@ -593,15 +597,40 @@ static int i8_setup(scs_problem* p) {
   scs_ctx* c = p->ctx;
   const int64_t m = p->m;
   p->ldx = round_up(p->ldd, kI8BK);
-  // shortest moduli prefix with P/2 > n * 2^(2b) for b >= the requested bits; b then takes all the headroom of that P
+  // column statistics first: they decide the moduli count
+  if (!p->d_colmax) SCS_TRY(dalloc(&p->d_colmax, m));
+  if (!p->d_colnorm2) SCS_TRY(dalloc(&p->d_colnorm2, m));
+  {
+    StageTimer t(c, ST_FWD);
+    LAUNCH(c, k_colabsmax, (unsigned)m, 256, 0, p->dA, p->ldd, p->n, (int)m, p->d_colmax, p->d_colnorm2);
+  }
+  std::vector<double> hmax(m), hn2(m);
+  CU_TRY(cudaMemcpyAsync(hmax.data(), p->d_colmax, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(hn2.data(), p->d_colnorm2, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  // r_j = max_i |A_ij| / ||A_j||_2 in (0, 1]: the largest entry of column j of X is T r_j
+  double rmax = 0.0;
+  for (int64_t j = 0; j < m; ++j)
+    if (hn2[j] > 0.0 && std::isfinite(hn2[j])) rmax = std::max(rmax, hmax[j] / std::sqrt(hn2[j]));
+  if (rmax == 0.0) rmax = 1.0;  // A = 0
+  // T_k: largest column norm the prefix of k moduli can hold: (T (1 + 1e-6) + sqrt(rows)/2)^2 < P_k / 2  (the 1e-6 covers
+  // the rounding of the norms and scales, sqrt(rows)/2 the rint of every entry).  Entries must stay below 2^50 (exact
+  // fp64 integer arithmetic in k_residues): T <= 2^50 / rmax.  Shortest prefix with T_k >= 2^bits, then all of that
+  // prefix's range is used.
+  const double T_cap = std::ldexp(1.0, 50) / rmax;
+  const double T_req = std::min(std::ldexp(1.0, p->i8_bits), T_cap);
+  auto T_of = [&](int k) {
+    return (std::exp2((h_log2P[k - kNModMin] - 1.0) / 2.0) - 0.5 * std::sqrt((double)p->ldx)) * (1.0 - 1e-6);
+  };
   int nmod = kNMod;
   for (int k = kNModMin; k <= kNMod; ++k)
-    if (h_log2P[k - kNModMin] - 1.0 - std::log2((double)p->ldx) >= 2.0 * p->i8_bits) {
+    if (T_of(k) >= T_req) {
       nmod = k;
       break;
     }
   p->i8_nmod = nmod;
-  p->i8_b = std::min((int)std::floor((h_log2P[nmod - kNModMin] - 1.0 - std::log2((double)p->ldx)) / 2.0), 50);
+  p->i8_T = std::min(T_of(nmod), T_cap);
+  p->i8_b = (int)std::floor(std::log2(p->i8_T));  // log2 of the column norm actually used
   const size_t plane_bytes = (size_t)nmod * p->ldx * m;
   I8Plan& pl = p->i8plan;
   pl.m = (int)m;
@@ -631,10 +660,9 @@ static int i8_setup(scs_problem* p) {
   CU_TRY(cudaMemsetAsync(p->d_planes, 0, plane_bytes, c->stream));
   CU_TRY(cudaMalloc((void**)&p->d_i8partial, partial_bytes));
   CU_TRY(cudaMemsetAsync(p->d_i8partial, 0, partial_bytes, c->stream));
-  SCS_TRY(dalloc(&p->d_colmax, m));
   SCS_TRY(dalloc(&p->d_wstat, 4));
   SCS_TRY(dalloc(&p->d_colscale, m));
-  CU_TRY(cudaMalloc((void**)&p->d_ecol, m * sizeof(int)));
+  SCS_TRY(dalloc(&p->d_colinv, m));
   CU_TRY(cudaMalloc((void**)&p->d_i8tiles, tiles.size() * sizeof(int2)));
   CU_TRY(cudaMalloc((void**)&p->d_i8progress, sizeof(unsigned long long)));
   CU_TRY(cudaMemcpyAsync(p->d_i8tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
@@ -655,10 +683,6 @@ static int i8_setup(scs_problem* p) {
   if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (int8 B slab) failed: " + std::to_string((int)r));
   CU_TRY(cudaFuncSetAttribute(k_i8syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes));
   CU_TRY(cudaFuncSetAttribute(k_i8syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8Smem2Bytes));
-  {
-    StageTimer t(c, ST_FWD);
-    LAUNCH(c, k_colabsmax, (unsigned)m, 256, 0, p->dA, p->ldd, p->n, (int)m, p->d_colmax);
-  }
   p->i8_ready = true;
   return SCS_OK;
 }
@@ -685,7 +709,8 @@ static int run_gram_i8(scs_problem* p, int* done) {
     CU_TRY(cudaMemcpyAsync(st, p->d_wstat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (!(st[1] >= 0.0) || !std::isfinite(st[0])) return SCS_OK;  // not eligible
-    LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, p->d_colmax, p->d_wstat, m, p->i8_b, p->d_ecol, p->d_colscale);
+    LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, (const double*)p->d_colnorm2, (const double*)p->d_wstat, m, p->i8_T,
+           p->d_colinv, p->d_colscale);
     const unsigned gx = (unsigned)((nproc / 8 + 255) / 256);
     const dim3 rgrid(gx, (unsigned)std::min(m, 64));
     switch (p->i8_nmod) {
@@ -746,7 +771,7 @@ static int run_gram_i8(scs_problem* p, int* done) {
   }
   {
     StageTimer t(c, ST_GRAMFIN);
-    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, p->d_ecol, p->i8_b, p->d_G);
+    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv, p->d_G);
   }
   *done = 1;
   return SCS_OK;
@@ -767,7 +792,7 @@ static int run_gram(scs_problem* p, XRef x) {
     {
       StageTimer t(c, ST_GRAM);
       const size_t smem = (size_t)m * sizeof(double);
-      static size_t attr_smem = 0;
+      size_t& attr_smem = c->sp_gram_smem;  // function attributes are per device: cached in the context
       if (smem > attr_smem) {
         if (smem > 220 * 1024) return fail(SCS_UNSUPPORTED, "sparse Gram: m > 28160 is not supported");
         CU_TRY(cudaFuncSetAttribute(k_sp_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -830,7 +855,7 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
   const int nblk = (m + kNB - 1) / kNB;
   {
-    static bool attr_set = false;
+    bool& attr_set = c->solve_attr_set;  // function attributes are per device: cached in the context
     if (!attr_set) {
       CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
       // same shared-memory carve-out for every kernel of the sequence: no SM reconfiguration between launches
@@ -924,7 +949,7 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
     int64_t ldm = m;
     int mm = m;
     const double* Wc = Wt;
-    static int p2p_capacity = -1;  // co-resident CTAs of k_bwd_p2p on this device
+    int& p2p_capacity = c->p2p_capacity;  // co-resident CTAs of k_bwd_p2p on this device
     if (p2p_capacity < 0) {
       int per_sm = 0;
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bwd_p2p, 256, 0));
@@ -1205,7 +1230,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_ecol, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
@@ -1615,7 +1640,7 @@ extern "C" int scs_get_stream_path(scs_problem* p, int* path) {
 }
 extern "C" int scs_set_gram_bits(scs_problem* p, int bits) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
-  if (bits < 24 || bits > 50) return fail(SCS_INVALID_ARG, "gram bits must be in 24..50");
+  if (bits < 24 || bits > 58) return fail(SCS_INVALID_ARG, "gram bits must be in 24..58");
   if (p->i8_ready) return fail(SCS_STATE_ERROR, "scs_set_gram_bits must be called before the first Gram");
   p->i8_bits = bits;
   return SCS_OK;

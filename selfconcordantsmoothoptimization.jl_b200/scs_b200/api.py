@@ -391,7 +391,8 @@ class Problem:
         return bool(a.value), b.value
 
     def set_gram_bits(self, bits):
-        """Fixed-point bits kept below each column's largest entry by the emulated-fp64 Gram (24..50, default 40)."""
+        """log2 of the common column 2-norm T of the fixed-point image the emulated-fp64 Gram works on (24..58, default 46:
+        Gram entries are off by ~0.4/T of the diagonal scale; see include/scs_b200.h)."""
         K.check(K.lib().scs_set_gram_bits(self._h, int(bits)))
         self.__dict__.setdefault("_modes", {})["set_gram_bits"] = bits
 
