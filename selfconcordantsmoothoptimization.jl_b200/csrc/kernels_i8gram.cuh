@@ -252,6 +252,15 @@ SCS_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = INT8, both K-major, N = 256, M = 128
 constexpr uint32_t kI8Idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kI8BN >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+// the same with N = 128: tiles on the diagonal whose right half lies above it
+constexpr uint32_t kI8IdescHalf = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((kI8BN / 2) >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+// Columns of the 128 x 256 tile of CTA `crank` of tile group (g, bj) that reach the lower triangle (col <= last row of the
+// tile): 0 = the whole tile lies above the diagonal (the CTA only relays its share of the B slab), <= 128 = N = 128 UMMAs.
+SCS_DEVINL int i8_live_cols(int2 tile, int crank) {
+  const int r1 = (tile.x * kI8Cluster + crank) * kI8BM + kI8BM;  // one past the last row
+  const int c0 = tile.y * kI8BN;
+  return max(0, min(kI8BN, r1 - c0));
+}
 
 SCS_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -335,6 +344,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
         int l = 0, c = 0, t = 0;
         if (valid) i8_unit(pl, u, l, c, t);
         const int2 tile = valid ? tiles[t] : make_int2(0, 0);
+        const bool live = i8_live_cols(tile, crank) > 0;
         const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         for (int sg = 0; sg < segs; ++sg) {
@@ -361,9 +371,9 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
           const int64_t s1 = s0 + kI8SegKb < kb1 ? s0 + kI8SegKb : kb1;
           for (int64_t kb = s0; kb < s1; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);  // all CTAs of the cluster have consumed this slot
-            mbar_expect_tx(&full[stage], kI8StageBytes);
+            mbar_expect_tx(&full[stage], live ? kI8StageBytes : kI8BBytes);
             uint8_t* sa = smem + stage * kI8StageBytes;
-            tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
+            if (live) tma_load_3d(sa, &xmap, &full[stage], (int)(kb * kI8BK), (tile.x * kI8Cluster + crank) * kI8BM, l);
             tma_load_3d_mc(sa + kI8ABytes + crank * (kI8BPart * kI8BK), &bmap, &full[stage], (int)(kb * kI8BK),
                            tile.y * kI8BN + crank * kI8BPart, l, kMask);
             if (++stage == kI8Stages) {
@@ -384,6 +394,8 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
       for (int64_t u = cid; u < pl.units; u += ncl) {
         int l, c, t;
         i8_unit(pl, u, l, c, t);
+        const int ncols = i8_live_cols(tiles[t], crank);
+        const uint32_t idesc = ncols > kI8BN / 2 ? kI8Idesc : kI8IdescHalf;
         const int64_t kb0 = pl.kb_lo + (int64_t)c * pl.chunk_kblocks;
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         mbar_wait(&acc_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -394,9 +406,11 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kI8StageBytes);
           const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kI8ABytes);
+          if (ncols > 0) {  // a tile above the diagonal issues nothing: the commit below releases the slot at once
 #pragma unroll
-          for (int k = 0; k < kI8BK / 32; ++k)
-            umma_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kI8Idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kI8BK / 32; ++k)
+              umma_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           tc_commit_mc(&empty[stage], kMask);  // tells every producer of the cluster that this CTA is done with the slot
           if (++stage == kI8Stages) {
             stage = 0;
@@ -425,8 +439,9 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
       const int jc = (tile.x * kI8Cluster + crank) * kI8BM + row_in_tile;
       int8_t* prow = partial + (((int64_t)l * pl.nchunks + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
       const uint32_t taddr = tmem_base + (uint32_t)(as * kI8BN) + ((uint32_t)(quarter * 32) << 16);
+      const int ncc = (i8_live_cols(tile, crank) + 31) / 32;  // column chunks that reach the lower triangle (k_crt reads kc <= jc)
 #pragma unroll 1
-      for (int cc = 0; cc < kI8BN / 32; ++cc) {
+      for (int cc = 0; cc < ncc; ++cc) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(cc * 32), v);
         uint32_t packed[8];
