@@ -839,13 +839,10 @@ static int run_gram(scs_problem* p, XRef x) {
   return SCS_OK;
 }
 
-// Solve M d = b on the device.  M (ld = m) is destroyed.  For the LU fallback the original must survive: sym = true
-// (M holds both triangles of a symmetric matrix): only the diagonal is saved (Msave: m doubles), the Cholesky never
-// writes the upper triangle; sym = false (only the lower triangle is trusted): Msave (m x m) receives a copy first.
-// b is destroyed; result in dsol.  tmp: m doubles.
-static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
-                     double* dsol, int m, int* used_fallback, bool sym) {
-  StageTimer t(c, ST_SOLVE);
+// Enqueues the factorisation part of run_solve (save, look-ahead or legacy Cholesky with the forward solve folded in) on
+// c->stream / c->stream2.  Capturable: no host synchronisation, the second stream forks from and re-joins the first.
+static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
+                        double* dsol, int m, bool sym, long long* d_prof) {
   if (sym)
     LAUNCH(c, k_save_diag, (m + 255) / 256, 256, 0, (const double*)M, (int64_t)m, m, Msave);
   else
@@ -854,29 +851,7 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
   CU_TRY(cudaMemcpyAsync(dsol, b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), c->stream));
   const int nblk = (m + kNB - 1) / kNB;
-  {
-    bool& attr_set = c->solve_attr_set;  // function attributes are per device: cached in the context
-    if (!attr_set) {
-      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
-      // same shared-memory carve-out for every kernel of the sequence: no SM reconfiguration between launches
-      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_bwd_all, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDiagSmem));
-      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr_set = true;
-    }
-  }
   double* rdiag = Linv;  // first m doubles of the workspace hold 1/L_jj
-  double* Wt = Linv + round_up(m, 16);  // (L_kk^-1)' per diagonal block (k_invdiag below)
-  long long* d_prof = nullptr;  // SCS_CHOL_PROF=1: clock64 stamps of the second k_chol_diag launch go to stderr
-  static const bool chol_prof = getenv("SCS_CHOL_PROF") && atoi(getenv("SCS_CHOL_PROF"));
-  if (chol_prof && c->solve_mode == 0) {
-    CU_TRY(cudaMalloc((void**)&d_prof, 16 * sizeof(long long)));
-    CU_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), c->stream));
-  }
   if (c->solve_mode == 0) {
     // look-ahead sequence (kernels_solve.cuh): diag -> trsm on the main stream, the trailing update of step k on the
     // second stream while diag(k+1) runs; trsm(k+1) waits for it.
@@ -924,6 +899,44 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
       }
     }
   }
+  return SCS_OK;
+}
+
+// Solve M d = b on the device.  M (ld = m) is destroyed.  For the LU fallback the original must survive: sym = true
+// (M holds both triangles of a symmetric matrix): only the diagonal is saved (Msave: m doubles), the Cholesky never
+// writes the upper triangle; sym = false (only the lower triangle is trusted): Msave (m x m) receives a copy first.
+// b is destroyed; result in dsol.  tmp: m doubles.
+// (Replaying the ~190 launches + event operations of the look-ahead sequence as one captured CUDA graph was measured
+// slower than issuing them: 3.45 vs 3.12 ms at m = 4096, 17.2 vs 15.4 ms at m = 8192 — the cross-branch graph edges cost
+// more than the stream-event waits; the sequence is therefore launched directly.)
+static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
+                     double* dsol, int m, int* used_fallback, bool sym) {
+  StageTimer t(c, ST_SOLVE);
+  const int nblk = (m + kNB - 1) / kNB;
+  {
+    bool& attr_set = c->solve_attr_set;  // function attributes are per device: cached in the context
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+      // same shared-memory carve-out for every kernel of the sequence: no SM reconfiguration between launches
+      CU_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_bwd_all, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDiagSmem));
+      CU_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU_TRY(cudaFuncSetAttribute(k_chol_trsm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr_set = true;
+    }
+  }
+  double* rdiag = Linv;  // first m doubles of the workspace hold 1/L_jj
+  double* Wt = Linv + round_up(m, 16);  // (L_kk^-1)' per diagonal block
+  long long* d_prof = nullptr;  // SCS_CHOL_PROF=1: clock64 stamps of the second k_chol_diag launch go to stderr
+  static const bool chol_prof = getenv("SCS_CHOL_PROF") && atoi(getenv("SCS_CHOL_PROF"));
+  if (chol_prof && c->solve_mode == 0) {
+    CU_TRY(cudaMalloc((void**)&d_prof, 16 * sizeof(long long)));
+    CU_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), c->stream));
+  }
+  SCS_TRY(chol_enqueue(c, M, Msave, Linv, d_info, b, tmp, dsol, m, sym, d_prof));
   int info = 0;
   CU_TRY(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));

@@ -137,6 +137,25 @@ def test_linear_solve_spd_and_indefinite(scs, m):
         assert relerr(d2, np.linalg.solve(Mi, b)) <= 1e-11 * np.linalg.cond(Mi)
 
 
+def test_linear_solve_legacy_sequence(scs, monkeypatch):
+    """SCS_SOLVE_LEGACY=1 (read when a context is created) selects the k_panel / k_syrk_update / k_bwd_all sequence the
+    look-ahead Cholesky replaced; both must solve the same systems."""
+    monkeypatch.setenv("SCS_SOLVE_LEGACY", "1")
+    ctx = scs.Context(0)
+    monkeypatch.delenv("SCS_SOLVE_LEGACY")
+    for m in (65, 200, 777):
+        rng = np.random.default_rng(m)
+        B = rng.standard_normal((m + 3, m))
+        M = B.T @ B + 0.5 * np.eye(m)
+        b = rng.standard_normal(m)
+        d_old, fb = ctx.linear_solve(M, b)
+        d_new, fb2 = scs.default_context().linear_solve(M, b)
+        assert not fb and not fb2
+        ref = np.linalg.solve(M, b)
+        assert relerr(d_old, ref) <= 1e-11 * np.linalg.cond(M) and relerr(d_new, ref) <= 1e-11 * np.linalg.cond(M)
+    ctx.close()
+
+
 def _mk(scs, m, reg, lam, **kw):
     A = synth.make_A(8, m)
     return scs.Problem(A, np.ones(8), np.zeros(m), scs.LeastSquaresLoss(8.0), lam, **kw)
