@@ -430,27 +430,34 @@ k_chol_diag(double* __restrict__ M, int64_t ld, int m, int k0, double* __restric
   SCS_STAMP(10);
 }
 
-// X L_kk' = A21 for the 64 rows [k0 + 64 + 64*blockIdx.x, ...): thread = row (the first two warps; all eight warps stage
-// L_kk), right-looking over the columns with the 64 entries of the row in registers and L_kk broadcast from shared
-// memory (LDS.128: measured faster than the 4-threads-per-row shuffle layout of k_panel, 9.5k vs 15.5k cycles), and the
-// update of the right-hand side below the block.  Block k is full (there are rows below it).
+// X L_kk' = A21 for the 64 rows [k0 + 64 + 64*blockIdx.x, ...) by substitution, right-looking over the columns, and the
+// update of the right-hand side below the block.  Two threads per row (the first four warps; all eight stage L_kk):
+// thread h of a row keeps the 32 entries of its row with column parity h in registers; column c is finished by its
+// owner (h = c & 1), handed to the partner lane with one shuffle, and both subtract it from their later columns with
+// L_kk broadcast from shared memory.  L_kk is stored parity-split (Lsm[c][h][k] = L[2k+h][c]) so that a 128-bit load
+// brings two entries of one parity: the kernel is bound by these broadcast LDS.128 (11 cycles each, measured), and the
+// split halves their number per warp (one thread per row with 64 registers: 9.5k cycles; the 4-threads-per-row
+// shuffle layout of k_panel: 15.5k).  Block k is full (there are rows below it).
 // kIdentity: the rows are those of the identity instead, for every diagonal block at once (k0 = 64*blockIdx.x), and
-// X = L_kk^-T is stored as Wt[blockIdx.x][r][c] — the layout k_bwd_all reads.
+// X = L_kk^-T is stored as Wt[blockIdx.x][r][c] — the layout k_bwd_all / k_bwd_p2p read.
 constexpr int kTrsmThreads = 256;
+constexpr int kLH = kNB / 2 + 2;  // doubles per (column, parity) slice: 32 entries + padding (even: 16-byte aligned slices,
+                                  // and the two parities of a column land in different banks)
 template <bool kIdentity>
 __global__ void __launch_bounds__(kTrsmThreads) k_chol_trsm(double* __restrict__ M, int64_t ld, int m, int k0_,
                                                             const double* __restrict__ rdiag_g,
                                                             double* __restrict__ bvec, const double* __restrict__ yvec,
                                                             double* __restrict__ Wt_all, long long* __restrict__ prof) {
-  __shared__ __align__(16) double Lsm[kNB * kNB];  // Lsm[c][cp] = L[k0+cp][k0+c]
+  __shared__ __align__(16) double Lsm[kNB * 2 * kLH];  // Lsm[(2c + h) * kLH + k] = L[k0 + 2k + h][k0 + c]
   __shared__ double rds[kNB], ys[kNB];
   const int tid = threadIdx.x;
   const int k0 = kIdentity ? (int)blockIdx.x * kNB : k0_;
   const int nb = min(kNB, m - k0);
-  const int row = k0 + kNB + (int)blockIdx.x * kNB + tid;
+  const int r = tid >> 1, h = tid & 1;  // row within the block and column parity (threads 0..127)
+  const int row = k0 + kNB + (int)blockIdx.x * kNB + r;
   if (blockIdx.x != 0) prof = nullptr;
   SCS_STAMP(0);
-  double x[kNB];
+  double x[kNB / 2];
   {
     const int i = tid & 63, pq = tid >> 6;
     double v[16];
@@ -459,43 +466,56 @@ __global__ void __launch_bounds__(kTrsmThreads) k_chol_trsm(double* __restrict__
       const int c = pq + 4 * u;
       v[u] = (i < nb && c < nb && i >= c) ? M[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
     }
-    if (tid < kNB) {
+    if (tid < 2 * kNB) {
 #pragma unroll
-      for (int c = 0; c < kNB; ++c) {
+      for (int k = 0; k < kNB / 2; ++k) {
+        const int c = 2 * k + h;
         if (kIdentity)
-          x[c] = c == tid ? 1.0 : 0.0;
+          x[k] = c == r ? 1.0 : 0.0;
         else
-          x[c] = row < m ? M[(int64_t)(k0 + c) * ld + row] : 0.0;
+          x[k] = row < m ? M[(int64_t)(k0 + c) * ld + row] : 0.0;
       }
+    }
+    if (tid < kNB) {
       rds[tid] = tid < nb ? rdiag_g[k0 + tid] : 1.0;
       ys[tid] = (!kIdentity && tid < nb) ? yvec[k0 + tid] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) Lsm[(pq + 4 * u) * kNB + i] = v[u];
+    for (int u = 0; u < 16; ++u) Lsm[(2 * (pq + 4 * u) + (i & 1)) * kLH + (i >> 1)] = v[u];
   }
   __syncthreads();
   SCS_STAMP(1);
-  if (tid >= kNB) return;
-  double s0 = 0.0, s1 = 0.0;
+  if (tid >= 2 * kNB) return;
+  const double* lh = Lsm + h * kLH;  // this thread's parity slices: lh[2 c kLH + k] = L[2k + h][c]
+  const int lane = tid & 31;
+  double sacc = 0.0;
 #pragma unroll
   for (int c = 0; c < kNB; ++c) {
-    x[c] *= rds[c];
-    if (c & 1)
-      s1 = fma(x[c], ys[c], s1);
-    else
-      s0 = fma(x[c], ys[c], s0);
+    const int ko = c >> 1, ho = c & 1;
+    const double xc = __shfl_sync(0xffffffffu, x[ko] * rds[c], (lane & ~1) | ho);  // the owner's finished entry
+    if (h == ho) {
+      x[ko] = xc;
+      sacc = fma(xc, ys[c], sacc);
+    }
+    const double* lc = lh + 2 * c * kLH;
+    if (ho == 0) {  // even column: the odd-parity thread still holds column c + 1 at index ko
+      if (h == 1) x[ko] = fma(-xc, lc[ko], x[ko]);
+    }
 #pragma unroll
-    for (int cp = c + 1; cp < kNB; ++cp) x[cp] = fma(-x[c], Lsm[c * kNB + cp], x[cp]);
+    for (int k = ko + 1; k < kNB / 2; ++k) x[k] = fma(-xc, lc[k], x[k]);
   }
   SCS_STAMP(2);
   if (kIdentity) {
     double* Wt = Wt_all + (int64_t)blockIdx.x * kNB * kNB;
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) Wt[tid * kNB + c] = x[c];
-  } else if (row < m) {
+    for (int k = 0; k < kNB / 2; ++k) Wt[r * kNB + 2 * k + h] = x[k];
+  } else {
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    if (row < m) {
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) M[(int64_t)(k0 + c) * ld + row] = x[c];
-    bvec[row] -= s0 + s1;
+      for (int k = 0; k < kNB / 2; ++k) M[(int64_t)(k0 + 2 * k + h) * ld + row] = x[k];
+      if (h == 0) bvec[row] -= sacc;
+    }
   }
   SCS_STAMP(3);
 }
