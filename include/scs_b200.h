@@ -128,8 +128,9 @@ int scs_set_gram_mode(scs_problem* p, int mode);
 int scs_get_gram_path(scs_problem* p, int* path);
 /* Fixed-point precision of the emulated-fp64 Gram.  The columns of diag(sqrt w) A are scaled to a common 2-norm T before
  * rounding to integers (then every entry of the integer Gram is below T^2, which is what the CRT range P/2 has to hold);
- * an entry of the Gram is off by ~0.4/T of the diagonal scale, whatever the number of rows.  `bits` = log2 of the T asked
- * for (24..58, default 46: ~3e-15, the rounding noise of an fp64 DGEMM over ~1000 rows; call before the first Gram).  The
+ * an entry of the Gram is off by ~0.4/T * sqrt(w_max / mean w) of the diagonal scale (standard deviation; the largest
+ * entry error is a few times that), whatever the number of rows.  `bits` = log2 of the T asked
+ * for (24..58, default 46: ~3e-15 rms, the rounding noise of an fp64 DGEMM over ~1000 rows; call before the first Gram).  The
  * library takes the shortest prefix of its 15 moduli that holds T (12 for the default), then uses all of that prefix's
  * range; single entries are capped at 2^50 (exact fp64 integers).  scs_get_gram_info reports the moduli count and
  * floor(log2 T) of the T actually used (0, 0 before the int8 path has run). */

@@ -16,8 +16,9 @@
 //      (P = prod p_l > 2 T^2) and writes G_jk = R / (s_j s_k) to both triangles.
 //
 // The only rounding is the fixed-point quantisation of C and the final conversion to fp64; the integer Gram itself is
-// exact and bit-reproducible.  The quantisation error of an entry is ~0.4 / T of the diagonal scale whatever n is
-// (12 moduli: T = 2^46.9 -> 3e-15; 13: 2e-16, i.e. fp64 rounding level).  The host picks the shortest moduli prefix whose
+// exact and bit-reproducible.  The quantisation error of an entry is ~0.4 / T of the diagonal scale (standard deviation, for
+// w = const; the maximum over all entries is a few times that) whatever n is (12 moduli: T = 2^46.9 -> 3e-15; 13: 2e-16,
+// i.e. fp64 rounding level).  The host picks the shortest moduli prefix whose
 // T leaves every column at least the requested bits below its largest entry (default 38: 12 moduli for Gaussian-like
 // columns at n = 1e6), then uses all of that prefix's range.
 #pragma once

@@ -2,7 +2,8 @@
 norm-equalised fixed point, residues modulo the library's moduli, Gram of residues, CRT.  It pins the two claims the
 GPU path rests on, independently of the hardware: (1) with columns scaled to a common 2-norm T every entry of X'X is
 below T^2 (Cauchy-Schwarz), so the symmetric CRT range P/2 > T^2 of the shortest sufficient moduli prefix recovers the
-integer Gram exactly; (2) the only error is the rounding of X, about 0.4/T of the diagonal scale whatever n is."""
+integer Gram exactly; (2) the only error is the rounding of X: 0.4/T * sqrt(w_max / mean w) of the diagonal scale per entry (standard
+deviation), a few times that for the worst entry, whatever n is."""
 import math
 
 import numpy as np
