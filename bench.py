@@ -404,7 +404,8 @@ def main():
             roof = {"bound": "tensor", "kernel": "k_i8syrk (tcgen05.mma kind::i8, TMA multicast, TMEM int32 accumulators)",
                     "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": traffic.get("k_i8syrk"),
                     "peak_source": i8_src, "algorithmic_ops_per_launch": ops, "ms_per_launch": g_ms / g_calls,
-                    "launches_timed": g_calls, "moduli": nmod, "fixed_point_bits": kept_bits}
+                    "launches_timed": g_calls, "moduli": nmod, "fixed_point_bits": kept_bits,
+                    "fixed_point_note": "floor(log2 T): columns of sqrt(w) A are scaled to the common 2-norm T before rounding"}
             tot = (g_ms + stages["residues"][0] + stages["gram_finalize"][0]) / g_calls
             fe = float(nl) * m * (m + 1) / (tot * 1e-3) / 1e12
             gram_equiv = {"what": "whole emulated-fp64 Gram (residues + int8 SYRK + CRT) as fp64-equivalent throughput",
