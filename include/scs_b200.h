@@ -136,6 +136,13 @@ int scs_get_gram_path(scs_problem* p, int* path);
  * floor(log2 T) of the T actually used (0, 0 before the int8 path has run). */
 int scs_set_gram_bits(scs_problem* p, int bits);
 int scs_get_gram_info(scs_problem* p, int* nmod, int* bits);
+/* Weights of both signs (the README's +-1-label cross-entropy pair, README.md:135-139 / test/test_algs.jl:9-11, makes
+ * Q_ii negative for part of the rows): the fixed-point image is built from sqrt(|w|) and the rows of the MINORITY sign
+ * are additionally compacted into a second set of planes, G = X'X - 2 Xc'Xc (or -X'X + 2 Xc'Xc when most rows are
+ * negative) — one int8 SYRK over all rows plus one over the compacted rows, combined exactly inside the CRT.
+ * Reports how the last emulated Gram ran: *compact_rows = rows in the compacted planes (-1: the weights had one sign),
+ * *minority_negative = 1 if those were the negative rows. */
+int scs_get_gram_signed(scs_problem* p, int64_t* compact_rows, int* minority_negative);
 /* Mini-batches (optim_loop!'s data loader, iterate.jl:139-145,204-207; utils.jl:18-25).  The host lays the rows of a
  * shard out batch after batch (after its one-time shuffle, if any); a batch is then a contiguous local row range.
  * scs_set_active_rows restricts every following pass (scs_step, scs_loss_eval, scs_gram, and scs_objective — the

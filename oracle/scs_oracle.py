@@ -710,12 +710,19 @@ def make_batches(n, batch_size=None, slice_samples=False, shuffle_batch=False, l
 
     MLUtils.DataLoader(batchsize=b, shuffle, partial=true) over n observations: ceil(n/b) consecutive batches of the
     (once) shuffled order, the last one possibly short.  `collect(loader)` runs the loader ONCE before the epoch
-    loop, so the same batches are reused in every epoch.  slice_samples (one row per step) yields to batch_size when
-    both are given (:127-130).  local_max_iter keeps only the first min(floor(local_max_iter), max_iter) batches
+    loop, so the same batches are reused in every epoch.  slice_samples yields to batch_size when both are given
+    (:127-130); on its own it steps on the first row only (see below).  local_max_iter keeps only the first min(floor(local_max_iter), max_iter) batches
     (:124,:127,:145).  The shuffle is Julia's RNG upstream; here the permutation is an explicit input (`perm`) so
     that the oracle and the GPU path see the same batches."""
     if batch_size is not None and slice_samples:
         slice_samples = False
+    # max_iter / iend are fixed BEFORE slice_samples sets opt.batch_size = 1 (:124-127 vs :136-138): without a
+    # batch_size max_iter stays 1, so `get_loader_subset(data, 1:iend)` (:145) keeps ONE entry — the whole data for the
+    # full-batch loader, only the FIRST ROW for slice_samples (the other rows never take part in a step).
+    max_iter = -(-n // int(batch_size)) if batch_size is not None else 1
+    iend = max_iter
+    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
+        iend = min(int(np.floor(local_max_iter)), max_iter)
     if slice_samples:
         batch_size = 1
         shuffle_batch = False
@@ -729,16 +736,14 @@ def make_batches(n, batch_size=None, slice_samples=False, shuffle_batch=False, l
             raise ValueError("shuffle_batch needs an explicit permutation (perm=) in this restatement")
         order = np.asarray(perm, dtype=np.int64)
         assert sorted(order.tolist()) == list(range(n))
-    max_iter = -(-n // batch_size)
-    iend = max_iter
-    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
-        iend = min(int(np.floor(local_max_iter)), max_iter)
     return [order[i * batch_size:min((i + 1) * batch_size, n)] for i in range(iend)]
 
 
 def iterate(method, model, reg_name, hmu, alpha=None, max_epoch=1000, x_tol=1e-10, f_tol=1e-10, batch_size=None,
             slice_samples=False, shuffle_batch=False, local_max_iter=None, perm=None):
     import copy
+    if local_max_iter is not None:  # iterate!: Options(max_epoch = local_max_iter !== nothing ? 1 : max_epoch) (:58-70)
+        max_epoch = 1
     if alpha is not None:  # iterate.jl:113-115
         model.L = 1 / alpha
     n = model.A.shape[0]

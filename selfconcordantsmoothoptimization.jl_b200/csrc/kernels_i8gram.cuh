@@ -62,6 +62,11 @@ struct I8Plan {
   int64_t chunk_kblocks;  // kI8ChunkRows / 128
   int64_t units;          // nmod * nchunks * ntiles
   int ldp;                // bytes per row of a partial-residue matrix
+  // partial-residue buffer: [nmod][pchunks][m][ldp]; this launch writes chunk slots pchunk0 .. pchunk0 + nchunks - 1.
+  // (signed weights: the compacted minority-sign rows are a second launch into the slots after the main ones)
+  int pchunks, pchunk0;
+  int main_chunks;        // k_crt: slots [0, main_chunks) carry weight sign_main, the rest sign_extra
+  int sign_main, sign_extra;
 };
 
 // ---- column / row statistics -------------------------------------------------------------------------------
@@ -98,38 +103,104 @@ __global__ void __launch_bounds__(256) k_colabsmax(const double* __restrict__ A,
     colnorm2[j] = s2;
   }
 }
-// stat[0] = max_i w_i, stat[1] = min_i w_i   (single CTA)
-__global__ void __launch_bounds__(kVecThreads) k_wstat(const double* __restrict__ w, int64_t n,
-                                                       double* __restrict__ stat) {
-  __shared__ double smax[32], smin[32];
-  double mx = -1e300, mn = 1e300;
-  for (int64_t i = threadIdx.x; i < n; i += kVecThreads) {
-    const double v = w[i];
-    mx = fmax(mx, v);
-    mn = fmin(mn, v);
-    if (v != v) mn = -1.0;  // NaN weights: not eligible
+// ---- weight statistics, entirely on the device (no host round trip per Gram) -----------------------------------
+// The rows are cut into blocks of kWsRows = 2048 (= one k_residues CTA: 256 threads x 8 rows).
+//   k_wstat_part : part[4b + {0: max |w|, 1: # rows with w < 0, 2: 1 if a weight is not finite}] for block b
+//   k_wstat_fin  : wstat[0] = max |w|, wstat[1] = # negative rows, wstat[2] = non-finite flag;
+//                  negbase[b] = # negative rows in blocks < b (exclusive scan: where block b's compacted rows start)
+constexpr int kWsRows = 2048;
+enum { WS_MAXABS = 0, WS_NNEG = 1, WS_BAD = 2, WS_COUNT = 4 };
+__global__ void __launch_bounds__(256) k_wstat_part(const double* __restrict__ w, int64_t nproc,
+                                                    double* __restrict__ part) {
+  __shared__ double smax[8], sneg[8], sbad[8];
+  const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  double mx = 0.0, neg = 0.0, bad = 0.0;
+  if (i0 < nproc) {  // nproc is a multiple of 16
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(w + i0 + q);
+      mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+      neg += (v.x < 0.0 ? 1.0 : 0.0) + (v.y < 0.0 ? 1.0 : 0.0);
+      if (!(fabs(v.x) < 1.0e300) || !(fabs(v.y) < 1.0e300)) bad = 1.0;  // NaN or Inf (fmax drops NaNs)
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    neg += __shfl_xor_sync(0xffffffffu, neg, o);
+    bad = fmax(bad, __shfl_xor_sync(0xffffffffu, bad, o));
   }
   if ((threadIdx.x & 31) == 0) {
     smax[threadIdx.x >> 5] = mx;
-    smin[threadIdx.x >> 5] = mn;
+    sneg[threadIdx.x >> 5] = neg;
+    sbad[threadIdx.x >> 5] = bad;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) {
+      mx = fmax(mx, smax[q]);
+      neg += sneg[q];
+      bad = fmax(bad, sbad[q]);
+    }
+    part[4 * blockIdx.x + 0] = mx;
+    part[4 * blockIdx.x + 1] = neg;
+    part[4 * blockIdx.x + 2] = bad;
+  }
+}
+__global__ void __launch_bounds__(kVecThreads) k_wstat_fin(const double* __restrict__ part, int nblk,
+                                                           double* __restrict__ wstat, int64_t* __restrict__ negbase) {
+  __shared__ double smax[32], sbad[32];
+  __shared__ long long ssum[32];
+  const int per = (nblk + kVecThreads - 1) / kVecThreads;  // consecutive blocks per thread
+  const int b0 = threadIdx.x * per, b1 = min(nblk, b0 + per);
+  double mx = 0.0, bad = 0.0;
+  long long cnt = 0;
+  for (int b = b0; b < b1; ++b) {
+    mx = fmax(mx, part[4 * b]);
+    cnt += (long long)part[4 * b + 1];
+    bad = fmax(bad, part[4 * b + 2]);
+  }
+  // exclusive scan of cnt over the threads
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad = fmax(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+  }
+  if (lane == 31) ssum[wid] = inc;
+  if (lane == 0) {
+    smax[wid] = mx;
+    sbad[wid] = bad;
+  }
+  __syncthreads();
+  long long base = 0, total = 0;
+  for (int q = 0; q < kVecThreads / 32; ++q) {
+    if (q < wid) base += ssum[q];
+    total += ssum[q];
+  }
+  long long run = base + inc - cnt;
+  for (int b = b0; b < b1; ++b) {
+    negbase[b] = run;
+    run += (long long)part[4 * b + 1];
+  }
+  if (threadIdx.x == 0) {
     for (int q = 1; q < kVecThreads / 32; ++q) {
       mx = fmax(mx, smax[q]);
-      mn = fmin(mn, smin[q]);
+      bad = fmax(bad, sbad[q]);
     }
-    stat[0] = mx;
-    stat[1] = mn;
+    wstat[WS_MAXABS] = mx;
+    wstat[WS_NNEG] = (double)total;
+    wstat[WS_BAD] = bad;
   }
 }
 // Norm-equalised fixed point: scale_j = T / (sqrt(wmax) * ||A_j||_2), so that every column of X = rint(C scale) has
-// ||X_j||_2 <= T (C = diag(sqrt w) A, w <= wmax) and, by Cauchy-Schwarz, every entry of X'X is below T^2 < P/2: the CRT
+// ||X_j||_2 <= T (C = diag(sqrt |w|) A, |w| <= wmax = stat[WS_MAXABS]) and, by Cauchy-Schwarz, every entry of X'X is below T^2 < P/2: the CRT
 // range is spent on precision, not on the worst case n * max^2.  inv_j = 1 / scale_j undoes it after the CRT.
 __global__ void k_colscale(const double* __restrict__ colnorm2, const double* __restrict__ stat, int m, double T,
                            double* __restrict__ inv, double* __restrict__ scale) {
@@ -149,26 +220,58 @@ __global__ void k_colscale(const double* __restrict__ colnorm2, const double* __
 //   r  = fma(-q, p, X)                    exact, |r| <= p/2 (+1 for p = 256 at a tie) -> its low byte is a valid residue
 //   lo32(r + M)                           two's-complement bits of r
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
-template <int NMOD>
+// SIGNED (weights of both signs, e.g. the README's +-1-label cross-entropy pair): X is built from sqrt(|w|), so
+//   G = sum_i w_i a_i a_i' = X'X - 2 * Xc'Xc   (Xc = the rows of X whose weight is negative),  or, when most rows are
+// negative,  G = -X'X + 2 * Xc'Xc  with Xc = the non-negative rows: the MINORITY sign is compacted.  Besides its plane
+// entries every thread writes its minority rows, byte by byte, to the compacted planes at
+//   cbase(block) + (# minority rows of the block before this thread) + ...   (consecutive threads -> consecutive bytes).
+template <int NMOD, bool SIGNED>
 __global__ void __launch_bounds__(256)
 k_residues(const double* __restrict__ A, int64_t ldd, int64_t nproc, int m, const double* __restrict__ w,
-           const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx) {
+           const double* __restrict__ scale, int8_t* __restrict__ planes, int64_t ldx,
+           const int64_t* __restrict__ negbase, int minor_neg, int8_t* __restrict__ cplanes, int64_t ldc) {
   __shared__ double s_p[NMOD], s_ip[NMOD];
+  __shared__ int s_wsum[8];
   if (threadIdx.x < NMOD) {
     s_p[threadIdx.x] = (double)c_mod_p[threadIdx.x];
     s_ip[threadIdx.x] = 1.0 / (double)c_mod_p[threadIdx.x];
   }
-  __syncthreads();
   const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-  if (i0 >= nproc) return;  // nproc is a multiple of 8; rows outside the active window have w = 0
+  const bool live = i0 < nproc;  // nproc is a multiple of 8; rows outside the active window have w = 0
   double sw[8];
+  uint32_t cmask = 0;  // SIGNED: which of this thread's rows go to the compacted planes
 #pragma unroll
   for (int q = 0; q < 8; q += 2) {
-    const double2 ww = *reinterpret_cast<const double2*>(w + i0 + q);
-    sw[q] = sqrt(ww.x);
-    sw[q + 1] = sqrt(ww.y);
+    const double2 ww = live ? *reinterpret_cast<const double2*>(w + i0 + q) : make_double2(0.0, 0.0);
+    sw[q] = sqrt(SIGNED ? fabs(ww.x) : ww.x);
+    sw[q + 1] = sqrt(SIGNED ? fabs(ww.y) : ww.y);
+    if (SIGNED && live) {
+      cmask |= ((ww.x < 0.0) == (minor_neg != 0) ? 1u : 0u) << q;
+      cmask |= ((ww.y < 0.0) == (minor_neg != 0) ? 1u : 0u) << (q + 1);
+    }
   }
+  int64_t cpos = 0;  // first compacted row of this thread
+  if (SIGNED) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int mine = __popc(cmask);
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    int before = inc - mine;
+    for (int q = 0; q < wid; ++q) before += s_wsum[q];
+    const int64_t nb = negbase[blockIdx.x];  // negative rows in earlier blocks
+    cpos = (minor_neg ? nb : (int64_t)blockIdx.x * kWsRows - nb) + before;
+  } else {
+    __syncthreads();
+  }
+  if (!live) return;
   const int64_t plane_stride = ldx * (int64_t)m;
+  const int64_t cplane_stride = ldc * (int64_t)m;
   for (int j = blockIdx.y; j < m; j += gridDim.y) {
     const double sc = scale[j];
     const double* col = A + (int64_t)j * ldd + i0;
@@ -180,6 +283,7 @@ k_residues(const double* __restrict__ A, int64_t ldd, int64_t nproc, int m, cons
       X[q + 1] = ((sw[q + 1] * a.y) * sc) + kMagic;
     }
     int8_t* dst = planes + (int64_t)j * ldx + i0;
+    int8_t* cdst = SIGNED ? cplanes + (int64_t)j * ldc + cpos : nullptr;
 #pragma unroll
     for (int l = 0; l < NMOD; ++l) {
       const double p = s_p[l], ip = s_ip[l];
@@ -194,8 +298,21 @@ k_residues(const double* __restrict__ A, int64_t ldd, int64_t nproc, int m, cons
       const uint32_t lo = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
       const uint32_t hi = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
       *reinterpret_cast<uint2*>(dst + (int64_t)l * plane_stride) = make_uint2(lo, hi);
+      if (SIGNED && cmask) {
+        int8_t* cd = cdst + (int64_t)l * cplane_stride;
+        int k = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if ((cmask >> q) & 1u) cd[k++] = (int8_t)(b[q] & 0xffu);
+      }
     }
   }
+}
+// zero the tail of the compacted planes up to the next 128-row k-block: rows [cnt, round_up(cnt, 128))
+__global__ void __launch_bounds__(128) k_cpad(int8_t* __restrict__ cplanes, int64_t ldc, int m, int64_t cnt) {
+  const int64_t pos = cnt + threadIdx.x;
+  const int64_t end = (cnt + 127) / 128 * 128;
+  if (pos < end) cplanes[((int64_t)blockIdx.y * m + blockIdx.x) * ldc + pos] = 0;
 }
 
 // ---- tcgen05 helpers -------------------------------------------------------------------------------------------
@@ -438,7 +555,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int jc = (tile.x * kI8Cluster + crank) * kI8BM + row_in_tile;
-      int8_t* prow = partial + (((int64_t)l * pl.nchunks + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
+      int8_t* prow = partial + (((int64_t)l * pl.pchunks + pl.pchunk0 + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
       const uint32_t taddr = tmem_base + (uint32_t)(as * kI8BN) + ((uint32_t)(quarter * 32) << 16);
       const int ncc = (i8_live_cols(tile, crank) + 31) / 32;  // column chunks that reach the lower triangle (k_crt reads kc <= jc)
 #pragma unroll 1
@@ -715,7 +832,7 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
       mbar_wait_bounded(&acc_full[as], aphase);
       tc_fence_after();
       const int jc = (tile.x * kI8Cluster + crank) * kI8BM + row_in_tile;
-      int8_t* prow = partial + (((int64_t)l * pl.nchunks + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
+      int8_t* prow = partial + (((int64_t)l * pl.pchunks + pl.pchunk0 + c) * pl.m + jc) * pl.ldp + (int64_t)tile.y * kI8BN;
       const uint32_t taddr = tmem_base + (uint32_t)(as * kI8BN) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kI8BN / 32; ++cc) {
@@ -767,10 +884,14 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
 // G[jc,kc] = G[kc,jc] = R * inv_jc * inv_kc.  One thread reconstructs 4 consecutive kc (32-bit loads of the
 // int8 partial residues).
 __global__ void __launch_bounds__(256)
-k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ inv, double* __restrict__ G) {
+k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ inv, const double* __restrict__ wstat,
+      int expect_nonneg, double* __restrict__ G) {
   const int kc0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
   const int jc = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (jc >= pl.m || kc0 >= pl.m || kc0 > jc) return;
+  // a non-finite weight poisons every entry of the fp64 Gram; so does (defensively) a negative weight on a path that
+  // was planned for non-negative ones — never a silently wrong matrix
+  const bool poisoned = wstat[WS_BAD] != 0.0 || (expect_nonneg && wstat[WS_NNEG] != 0.0);
   const int64_t cstride = (int64_t)pl.m * pl.ldp;
   unsigned __int128 acc[4] = {0, 0, 0, 0};
   double frac[4] = {0.0, 0.0, 0.0, 0.0};
@@ -778,14 +899,15 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ 
 #pragma unroll 1
   for (int l = 0; l < pl.nmod; ++l) {
     const int p = c_mod_p[l], ql = c_mod_q[var][l];
-    const int8_t* src = partial + ((int64_t)l * pl.nchunks * pl.m + jc) * pl.ldp + kc0;
+    const int8_t* src = partial + ((int64_t)l * pl.pchunks * pl.m + jc) * pl.ldp + kc0;
     int s[4] = {0, 0, 0, 0};
-    for (int c = 0; c < pl.nchunks; ++c) {
+    for (int c = 0; c < pl.pchunks; ++c) {
       const uint32_t v = *reinterpret_cast<const uint32_t*>(src + c * cstride);
-      s[0] += (int)(int8_t)(v & 0xff);
-      s[1] += (int)(int8_t)((v >> 8) & 0xff);
-      s[2] += (int)(int8_t)((v >> 16) & 0xff);
-      s[3] += (int)(int8_t)(v >> 24);
+      const int sg = c < pl.main_chunks ? pl.sign_main : pl.sign_extra;
+      s[0] += sg * (int)(int8_t)(v & 0xff);
+      s[1] += sg * (int)(int8_t)((v >> 8) & 0xff);
+      s[2] += sg * (int)(int8_t)((v >> 16) & 0xff);
+      s[3] += sg * (int)(int8_t)(v >> 24);
     }
     const unsigned __int128 Ml = ((unsigned __int128)c_mod_Mhi[var][l] << 64) | c_mod_Mlo[var][l];
     const double ipd = 1.0 / (double)p;
@@ -814,7 +936,8 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ 
     const unsigned __int128 mag = neg ? (unsigned __int128)(-r) : (unsigned __int128)r;
     double d = ldexp((double)(unsigned long long)(mag >> 64), 64) + (double)(unsigned long long)mag;
     if (neg) d = -d;
-    const double g = (d * ij) * inv[kc];
+    double g = (d * ij) * inv[kc];
+    if (poisoned) g = __longlong_as_double(0x7ff8000000000000LL);
     G[(int64_t)kc * pl.m + jc] = g;
     G[(int64_t)jc * pl.m + kc] = g;
   }

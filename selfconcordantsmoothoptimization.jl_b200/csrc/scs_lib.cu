@@ -84,7 +84,7 @@ struct scs_ctx {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> ev_pool;
   EncodeTiledFn encode = nullptr;
-  // scratch for scs_linear_solve
+  double* d_flag = nullptr;  // one device double: cross-rank agreement on a status (agree_ok)
 };
 
 struct StageTimer {  // records an event pair around a stage when profiling is on
@@ -148,6 +148,20 @@ static int allreduce(scs_ctx* c, double* buf, size_t count) {
   if (r != 0) return fail(SCS_NCCL_ERROR, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
   return SCS_OK;
 }
+// A status that can differ from rank to rank (out of memory, an unsupported shape) must be agreed on BEFORE the next
+// collective: a rank that returned early would leave its peers blocked inside NCCL.  *all_ok = every rank passed.
+static int agree_ok(scs_ctx* c, bool local_ok, bool* all_ok) {
+  *all_ok = local_ok;
+  if (c->world <= 1) return SCS_OK;
+  const double v = local_ok ? 0.0 : 1.0;
+  double tot = 0.0;
+  CU_TRY(cudaMemcpyAsync(c->d_flag, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SCS_TRY(allreduce(c, c->d_flag, 1));
+  CU_TRY(cudaMemcpyAsync(&tot, c->d_flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  *all_ok = tot == 0.0;
+  return SCS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // problem
@@ -202,6 +216,15 @@ struct scs_problem {
   int last_gram_path = 0;  // 1 DMMA, 2 int8
   bool i8_ready = false, i8_failed = false, i8_planes_valid = false;
   int8_t *d_planes = nullptr, *d_i8partial = nullptr;
+  // signed weights: compacted planes of the minority-sign rows (i8_setup_signed), per-block statistics
+  int8_t* d_cplanes = nullptr;
+  int64_t ldc = 0, i8_ccount = 0;
+  int64_t* d_negbase = nullptr;
+  double* d_wpart = nullptr;
+  bool i8_signed = false, i8_minor_neg = true;
+  int i8_pchunks_cap = 0;
+  CUtensorMap cmap{}, cmap_b{};
+  bool labels_unit = false;  // every label lies in [-1, 1] (checked at upload): consistent-mode GGN weights are >= 0
   double *d_colmax = nullptr, *d_wstat = nullptr, *d_colscale = nullptr;
   double *d_colinv = nullptr, *d_colnorm2 = nullptr;
   double i8_T = 0.0;  // column 2-norm target of the fixed-point image (run_gram_i8)
@@ -315,17 +338,23 @@ static int allreduce(scs_ctx* c, double* buf, size_t count);
 // Select the rows that take part in the following passes.  Everything cached for the previous window is dropped.
 static int set_window(scs_problem* p, int64_t lo, int64_t hi, int64_t rows_global = -1) {
   if (lo < 0 || hi < lo || hi > p->n) return fail(SCS_INVALID_ARG, "row window outside the shard");
-  if (lo == p->win_lo && hi == p->win_hi && p->win_rows_global > 0) return SCS_OK;
-  p->win_lo = lo;
-  p->win_hi = hi;
-  p->alo = lo / 128 * 128;
-  p->ahi = hi > lo ? std::min(round_up(hi, 128), p->ldd) : p->alo;
-  p->fwd_id = 0;
-  p->grad_id = 0;
-  p->gq_id = 0;
-  p->gqprev_id = 0;
-  p->loss_reduced = false;
-  p->i8_planes_valid = false;
+  // Unchanged window: nothing to recompute — but with several ranks and no global row count from the caller the
+  // all-reduce below must still be entered by EVERY rank, whatever its local window looks like (a rank whose slice of
+  // two consecutive batches is empty at the same offset would otherwise skip it and hang the others).
+  const bool same = lo == p->win_lo && hi == p->win_hi && p->win_rows_global > 0;
+  if (same && (rows_global >= 0 || p->ctx->world == 1)) return SCS_OK;
+  if (!same) {
+    p->win_lo = lo;
+    p->win_hi = hi;
+    p->alo = lo / 128 * 128;
+    p->ahi = hi > lo ? std::min(round_up(hi, 128), p->ldd) : p->alo;
+    p->fwd_id = 0;
+    p->grad_id = 0;
+    p->gq_id = 0;
+    p->gqprev_id = 0;
+    p->loss_reduced = false;
+    p->i8_planes_valid = false;
+  }
   p->win_rows_global = rows_global >= 0 ? rows_global : hi - lo;
   if (p->ctx->world > 1 && rows_global < 0) {  // the GGN wide-branch test needs the global batch size
     const double v = (double)(hi - lo);
@@ -652,15 +681,26 @@ static int i8_setup(scs_problem* p) {
   const size_t partial_bytes = (size_t)nmod * pl.nchunks * m * pl.ldp;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  if (plane_bytes + partial_bytes + (2ull << 30) > free_b) {
+  bool fits = plane_bytes + partial_bytes + (2ull << 30) <= free_b, all_fit = true;
+  SCS_TRY(agree_ok(c, fits, &all_fit));  // every rank takes the same Gram path: the all-reduce of G follows
+  if (!all_fit) {
     p->i8_failed = true;
-    return fail(SCS_OOM, "not enough HBM for the int8 residue planes");
+    char msg[256];
+    snprintf(msg, sizeof(msg), "not enough HBM for the int8 residue planes (%s: %.1f GB planes + %.1f GB partials, %.1f GB free)",
+             fits ? "on another rank" : "this rank", plane_bytes / 1e9, partial_bytes / 1e9, free_b / 1e9);
+    return fail(SCS_OOM, msg);
   }
   CU_TRY(cudaMalloc((void**)&p->d_planes, plane_bytes));
   CU_TRY(cudaMemsetAsync(p->d_planes, 0, plane_bytes, c->stream));
   CU_TRY(cudaMalloc((void**)&p->d_i8partial, partial_bytes));
   CU_TRY(cudaMemsetAsync(p->d_i8partial, 0, partial_bytes, c->stream));
-  SCS_TRY(dalloc(&p->d_wstat, 4));
+  SCS_TRY(dalloc(&p->d_wstat, WS_COUNT));
+  {
+    const size_t nblk = (size_t)((p->ldd + kWsRows - 1) / kWsRows);
+    SCS_TRY(dalloc(&p->d_wpart, 4 * nblk));
+    CU_TRY(cudaMalloc((void**)&p->d_negbase, (nblk + 1) * sizeof(int64_t)));
+  }
+  p->i8_pchunks_cap = pl.nchunks;
   SCS_TRY(dalloc(&p->d_colscale, m));
   SCS_TRY(dalloc(&p->d_colinv, m));
   CU_TRY(cudaMalloc((void**)&p->d_i8tiles, tiles.size() * sizeof(int2)));
@@ -687,7 +727,98 @@ static int i8_setup(scs_problem* p) {
   return SCS_OK;
 }
 
-// returns *done = 0 when the weights are not eligible (negative / NaN): the caller then runs the DMMA kernel
+// Compacted planes for the minority-sign rows of a signed Gram (allocated on first use: at most half of the rows, +50 %
+// plane memory) and a partial-residue buffer with room for their chunks.
+static int i8_setup_signed(scs_problem* p) {
+  if (p->d_cplanes) return SCS_OK;
+  scs_ctx* c = p->ctx;
+  const int64_t m = p->m;
+  p->ldc = round_up(p->ldx / 2 + kI8BK, kI8BK);
+  const I8Plan& pl = p->i8plan;
+  const int cchunks = (int)((p->ldc / kI8BK + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
+  const size_t cbytes = (size_t)pl.nmod * p->ldc * m;
+  const size_t partial_bytes = (size_t)pl.nmod * (pl.nchunks + cchunks) * m * pl.ldp;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t have = (size_t)pl.nmod * pl.nchunks * m * pl.ldp;  // the partial buffer is re-allocated
+  if (cbytes + partial_bytes + (2ull << 30) > free_b + have)
+    return fail(SCS_OOM, "not enough HBM for the compacted planes of a signed int8 Gram");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  dfree(p->d_i8partial);
+  p->d_i8partial = nullptr;
+  CU_TRY(cudaMalloc((void**)&p->d_i8partial, partial_bytes));
+  CU_TRY(cudaMemsetAsync(p->d_i8partial, 0, partial_bytes, c->stream));
+  CU_TRY(cudaMalloc((void**)&p->d_cplanes, cbytes));
+  p->i8_pchunks_cap = pl.nchunks + cchunks;
+  cuuint64_t gdim[3] = {(cuuint64_t)p->ldc, (cuuint64_t)m, (cuuint64_t)pl.nmod};
+  cuuint64_t gstride[2] = {(cuuint64_t)p->ldc, (cuuint64_t)p->ldc * (cuuint64_t)m};
+  cuuint32_t box[3] = {(cuuint32_t)kI8BK, 128u, 1u};
+  cuuint32_t boxb[3] = {(cuuint32_t)kI8BK, (cuuint32_t)kI8BPart, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(&p->cmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, p->d_cplanes, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS)
+    r = c->encode(&p->cmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, p->d_cplanes, gdim, gstride, boxb, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (compacted planes) failed: " + std::to_string((int)r));
+  return SCS_OK;
+}
+
+// Are the Gram weights of kind `wk` non-negative by construction?  Then nothing about them has to come back to the
+// host before the kernels are queued.  Newton weights p*y^2*e/(1+e)^2, least squares 1/p, and the GGN weights of the
+// consistent cross-entropy (yc = (y+1)/2 in [0,1]) are; the README's literal +-1-label pair is not.
+static bool weights_nonneg_apriori(const scs_problem* p, int wk) {
+  if (!(p->loss.p > 0.0)) return false;
+  if (p->loss.kind == SCS_LOSS_LEASTSQUARES) return true;
+  if (p->loss.kind != SCS_LOSS_LOGISTIC) return false;
+  if (wk == SCS_WEIGHTS_NEWTON) return true;
+  return p->loss.label_mode == SCS_LABELS_CONSISTENT && p->labels_unit;
+}
+
+static int i8_launch_syrk(scs_problem* p, const CUtensorMap& amap, const CUtensorMap& bmap, const I8Plan& pl) {
+  scs_ctx* c = p->ctx;
+  // SCS_I8_2CTA=1 selects the cta_group::2 SYRK (kernels_i8gram.cuh).  Measured equal to the 1-CTA kernel on this part
+  // (C2: 104.0 vs 104.9 ms, both power-capped at 1.56 GHz; 400k x 2048: 11.1 vs 10.6 ms), so the default stays 1-CTA.
+  static const bool two_cta = []() {
+    const char* e = getenv("SCS_I8_2CTA");
+    return e && e[0] == '1';
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(c->num_sms / kI8Cluster * kI8Cluster));
+  cfg.blockDim = dim3(kI8Threads);
+  cfg.dynamicSmemBytes = two_cta ? kI8Smem2Bytes : kI8SmemBytes;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kI8Cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent kernel: exactly as many clusters as can be co-resident (GPC shapes strand some SMs for clusters of 4)
+  if (p->i8_clusters == 0) {
+    int nc = 0;
+    cudaError_t oe = two_cta ? cudaOccupancyMaxActiveClusters(&nc, k_i8syrk2, &cfg)
+                             : cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg);
+    if (oe != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
+    p->i8_clusters = nc;
+  }
+  const int ncl = (int)std::min<int64_t>(p->i8_clusters, pl.units);
+  cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
+  CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
+  cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, amap, bmap, pl, (const int2*)p->d_i8tiles,
+                                                p->d_i8partial, p->d_i8progress)
+                           : cudaLaunchKernelEx(&cfg, k_i8syrk, amap, bmap, pl, (const int2*)p->d_i8tiles,
+                                                p->d_i8partial, p->d_i8progress);
+  c->launches += 1;
+  if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
+  return SCS_OK;
+}
+
+// returns *done = 0 when this call cannot be served (non-finite weights, or no memory for the compacted planes of a
+// signed Gram): the caller then runs the DMMA kernel
 static int run_gram_i8(scs_problem* p, int* done) {
   scs_ctx* c = p->ctx;
   *done = 0;
@@ -702,22 +833,44 @@ static int run_gram_i8(scs_problem* p, int* done) {
   pl.kblocks = pl.kb_lo + (nproc + kI8BK - 1) / kI8BK;
   pl.nchunks = (int)((pl.kblocks - pl.kb_lo + pl.chunk_kblocks - 1) / pl.chunk_kblocks);
   pl.units = (int64_t)pl.nmod * pl.nchunks * pl.ntiles;
+  const bool nonneg = weights_nonneg_apriori(p, p->fwd_wk);
   if (!(const_w && p->i8_planes_valid)) {
     StageTimer t(c, ST_RESID);
-    LAUNCH(c, k_wstat, 1, kVecThreads, 0, p->dw + p->alo, nproc, p->d_wstat);
-    double st[2];
-    CU_TRY(cudaMemcpyAsync(st, p->d_wstat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    if (!(st[1] >= 0.0) || !std::isfinite(st[0])) return SCS_OK;  // not eligible
+    const int nblk = (int)((nproc + kWsRows - 1) / kWsRows);
+    LAUNCH(c, k_wstat_part, nblk, 256, 0, (const double*)(p->dw + p->alo), nproc, p->d_wpart);
+    LAUNCH(c, k_wstat_fin, 1, kVecThreads, 0, (const double*)p->d_wpart, nblk, p->d_wstat, p->d_negbase);
+    p->i8_signed = false;
+    p->i8_minor_neg = true;
+    p->i8_ccount = 0;
+    if (!nonneg) {  // the sign pattern decides the launch plan: one small read-back (the a-priori case has none)
+      double st[WS_COUNT];
+      CU_TRY(cudaMemcpyAsync(st, p->d_wstat, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(cudaStreamSynchronize(c->stream));
+      if (st[WS_BAD] != 0.0) return SCS_OK;  // NaN / Inf weights: the fp64 kernel propagates them
+      const int64_t nneg = (int64_t)(st[WS_NNEG] + 0.5);
+      if (nneg > 0) {
+        int rc = i8_setup_signed(p);
+        if (rc == SCS_OOM) return SCS_OK;
+        SCS_TRY(rc);
+        p->i8_signed = true;
+        p->i8_minor_neg = nneg <= nproc - nneg;
+        p->i8_ccount = p->i8_minor_neg ? nneg : nproc - nneg;
+      }
+    }
     LAUNCH(c, k_colscale, (m + 255) / 256, 256, 0, (const double*)p->d_colnorm2, (const double*)p->d_wstat, m, p->i8_T,
            p->d_colinv, p->d_colscale);
-    const unsigned gx = (unsigned)((nproc / 8 + 255) / 256);
+    const unsigned gx = (unsigned)nblk;
     const dim3 rgrid(gx, (unsigned)std::min(m, 64));
     switch (p->i8_nmod) {
-#define SCS_RES_CASE(K)                                                                                            \
-  case K:                                                                                                          \
-    LAUNCH(c, k_residues<K>, rgrid, 256, 0, p->dA + p->alo, p->ldd, nproc, m, p->dw + p->alo, p->d_colscale,      \
-           p->d_planes + p->alo, p->ldx);                                                                        \
+#define SCS_RES_CASE(K)                                                                                                \
+  case K:                                                                                                              \
+    if (p->i8_signed)                                                                                                  \
+      LAUNCH(c, (k_residues<K, true>), rgrid, 256, 0, p->dA + p->alo, p->ldd, nproc, m, p->dw + p->alo, p->d_colscale, \
+             p->d_planes + p->alo, p->ldx, (const int64_t*)p->d_negbase, p->i8_minor_neg ? 1 : 0, p->d_cplanes,       \
+             p->ldc);                                                                                                  \
+    else                                                                                                               \
+      LAUNCH(c, (k_residues<K, false>), rgrid, 256, 0, p->dA + p->alo, p->ldd, nproc, m, p->dw + p->alo,              \
+             p->d_colscale, p->d_planes + p->alo, p->ldx, (const int64_t*)nullptr, 0, (int8_t*)nullptr, (int64_t)0);  \
     break;
       SCS_RES_CASE(10)
       SCS_RES_CASE(11)
@@ -729,49 +882,32 @@ static int run_gram_i8(scs_problem* p, int* done) {
       default:
         return fail(SCS_STATE_ERROR, "int8 Gram: bad moduli count");
     }
+    if (p->i8_signed && p->i8_ccount % kI8BK)
+      LAUNCH(c, k_cpad, dim3(m, p->i8_nmod), 128, 0, p->d_cplanes, p->ldc, m, p->i8_ccount);
     p->i8_planes_valid = true;
   }
+  // chunk slots of the partial-residue buffer: the main SYRK first, then the compacted rows
+  I8Plan cpl = pl;
+  cpl.kb_lo = 0;
+  cpl.kblocks = (p->i8_ccount + kI8BK - 1) / kI8BK;
+  cpl.nchunks = p->i8_signed ? (int)((cpl.kblocks + cpl.chunk_kblocks - 1) / cpl.chunk_kblocks) : 0;
+  cpl.units = (int64_t)cpl.nmod * cpl.nchunks * cpl.ntiles;
+  pl.pchunks = cpl.pchunks = pl.nchunks + cpl.nchunks;
+  pl.pchunk0 = 0;
+  cpl.pchunk0 = pl.nchunks;
+  pl.main_chunks = cpl.main_chunks = pl.nchunks;
+  pl.sign_main = cpl.sign_main = (p->i8_signed && !p->i8_minor_neg) ? -1 : 1;
+  pl.sign_extra = cpl.sign_extra = p->i8_minor_neg ? -2 : 2;
+  if (pl.pchunks > p->i8_pchunks_cap) return fail(SCS_STATE_ERROR, "int8 Gram: partial-residue buffer too small");
   {
     StageTimer t(c, ST_GRAM);
-    // SCS_I8_2CTA=1 selects the cta_group::2 SYRK (kernels_i8gram.cuh).  Measured equal to the 1-CTA kernel on this part
-    // (C2: 104.0 vs 104.9 ms, both power-capped at 1.56 GHz; 400k x 2048: 11.1 vs 10.6 ms), so the default stays 1-CTA.
-    static const bool two_cta = []() {
-      const char* e = getenv("SCS_I8_2CTA");
-      return e && e[0] == '1';
-    }();
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(c->num_sms / kI8Cluster * kI8Cluster));
-    cfg.blockDim = dim3(kI8Threads);
-    cfg.dynamicSmemBytes = two_cta ? kI8Smem2Bytes : kI8SmemBytes;
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kI8Cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // persistent kernel: exactly as many clusters as can be co-resident (GPC shapes strand some SMs for clusters of 4)
-    if (p->i8_clusters == 0) {
-      int nc = 0;
-      cudaError_t oe = two_cta ? cudaOccupancyMaxActiveClusters(&nc, k_i8syrk2, &cfg)
-                               : cudaOccupancyMaxActiveClusters(&nc, k_i8syrk, &cfg);
-      if (oe != cudaSuccess || nc < 1) nc = c->num_sms / kI8Cluster / 2;
-      p->i8_clusters = nc;
-    }
-    const int ncl = (int)std::min<int64_t>(p->i8_clusters, pl.units);
-    cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
-    CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
-    cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
-                                                  p->d_i8partial, p->d_i8progress)
-                             : cudaLaunchKernelEx(&cfg, k_i8syrk, p->xmap, p->xmap_b, pl, (const int2*)p->d_i8tiles,
-                                                  p->d_i8partial, p->d_i8progress);
-    c->launches += 1;
-    if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
+    SCS_TRY(i8_launch_syrk(p, p->xmap, p->xmap_b, pl));
+    if (cpl.nchunks > 0) SCS_TRY(i8_launch_syrk(p, p->cmap, p->cmap_b, cpl));
   }
   {
     StageTimer t(c, ST_GRAMFIN);
-    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv, p->d_G);
+    LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv,
+           (const double*)p->d_wstat, nonneg ? 1 : 0, p->d_G);
   }
   *done = 1;
   return SCS_OK;
@@ -816,6 +952,9 @@ static int run_gram(scs_problem* p, XRef x) {
     int done = 0;
     int rc = run_gram_i8(p, &done);
     if (rc != SCS_OK && !(rc == SCS_OOM && p->gram_mode == 0)) return rc;
+    if (rc == SCS_OOM)  // auto mode: say so once — the DMMA kernel is ~4x slower, a silent downgrade would look like a regression
+      fprintf(stderr, "[scs_b200] rank %d: %s; the Gram falls back to the native fp64 (DMMA) kernel for this problem\n",
+              c->rank, g_err.c_str());
     if (done) {
       p->last_gram_path = 2;
       SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
@@ -1103,6 +1242,7 @@ extern "C" int scs_ctx_create(int device, int rank, int world, const void* id128
     CU_TRY(cudaEventCreateWithFlags(&c->ev_upd[i], cudaEventDisableTiming));
   }
   if (const char* e = getenv("SCS_SOLVE_LEGACY")) c->solve_mode = atoi(e) ? 1 : 0;
+  CU_TRY(cudaMalloc((void**)&c->d_flag, sizeof(double)));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -1139,6 +1279,7 @@ extern "C" int scs_ctx_destroy(scs_ctx* c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->d_flag) cudaFree(c->d_flag);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_trsm[i]) cudaEventDestroy(c->ev_trsm[i]);
     if (c->ev_upd[i]) cudaEventDestroy(c->ev_upd[i]);
@@ -1243,12 +1384,18 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
   delete p;
   return SCS_OK;
+}
+
+static bool labels_in_unit_range(const double* y, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    if (!(y[i] >= -1.0 && y[i] <= 1.0)) return false;
+  return true;
 }
 
 extern "C" int scs_problem_create(scs_ctx* ctx, const double* A, int64_t n_local, int64_t m, int64_t lda,
@@ -1265,6 +1412,7 @@ extern "C" int scs_problem_create(scs_ctx* ctx, const double* A, int64_t n_local
     return s;
   }
   scs_problem* p = *out;
+  p->labels_unit = labels_in_unit_range(y, n_local);
   cudaError_t e = cudaMemcpy2DAsync(p->dA, p->ldd * sizeof(double), A, lda * sizeof(double),
                                     n_local * sizeof(double), m, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess)
@@ -1314,6 +1462,7 @@ extern "C" int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const
     *out = nullptr;
     return fail(e == cudaErrorMemoryAllocation ? SCS_OOM : SCS_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
   };
+  p->labels_unit = labels_in_unit_range(y, n_local);
   cudaError_t e = cudaMemcpyAsync(p->dy, y, n_local * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) return bail(e, "upload of y failed");
   // zero-based CSC on the host (32-bit row indices), then CSR by a counting pass (columns ascend inside every row)
@@ -1413,6 +1562,7 @@ extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64
          loss_kind == SCS_LOSS_LOGISTIC ? 0 : 1, 0.1);
   CU_TRY(cudaMemsetAsync(p->dz, 0, p->ldd * sizeof(double), ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  p->labels_unit = loss_kind == SCS_LOSS_LOGISTIC;  // k_synth_y draws +-1 labels
   return SCS_OK;
 }
 
@@ -1662,6 +1812,12 @@ extern "C" int scs_get_gram_info(scs_problem* p, int* nmod, int* bits) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   if (nmod) *nmod = p->i8_nmod;
   if (bits) *bits = p->i8_b;
+  return SCS_OK;
+}
+extern "C" int scs_get_gram_signed(scs_problem* p, int64_t* compact_rows, int* minority_negative) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (compact_rows) *compact_rows = p->i8_signed ? p->i8_ccount : -1;
+  if (minority_negative) *minority_negative = p->i8_minor_neg ? 1 : 0;
   return SCS_OK;
 }
 extern "C" int scs_get_gram_path(scs_problem* p, int* path) {

@@ -28,7 +28,7 @@ EXPORTS = (
     "scs_version", "scs_last_error", "scs_comm_unique_id", "scs_ctx_create", "scs_ctx_destroy", "scs_ctx_sync",
     "scs_ctx_stream", "scs_problem_create", "scs_problem_create_csc", "scs_problem_is_sparse", "scs_problem_create_synthetic", "scs_problem_destroy",
     "scs_problem_read_rows", "scs_set_regularizer", "scs_set_smoother", "scs_set_method", "scs_set_L",
-    "scs_set_gram_mode", "scs_get_gram_path", "scs_set_gram_bits", "scs_get_gram_info", "scs_set_stream_mode", "scs_get_stream_path", "scs_set_active_rows", "scs_set_batches", "scs_set_test_problem", "scs_get_test_history", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
+    "scs_set_gram_mode", "scs_get_gram_path", "scs_set_gram_bits", "scs_get_gram_info", "scs_get_gram_signed", "scs_set_stream_mode", "scs_get_stream_path", "scs_set_active_rows", "scs_set_batches", "scs_set_test_problem", "scs_get_test_history", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
     "scs_smoother_eval", "scs_prox", "scs_reg_value", "scs_get_counters", "scs_set_profiling", "scs_get_stage_ms",
 )
 
@@ -84,6 +84,7 @@ def lib():
         "scs_get_gram_path": ([vp, C.POINTER(i32)], i32),
         "scs_set_gram_bits": ([vp, i32], i32),
         "scs_get_gram_info": ([vp, C.POINTER(i32), C.POINTER(i32)], i32),
+        "scs_get_gram_signed": ([vp, _ip, C.POINTER(i32)], i32),
         "scs_set_test_problem": ([vp, vp], i32),
         "scs_get_test_history": ([vp, _dp, i64, _ip], i32),
         "scs_set_active_rows": ([vp, i64, i64], i32),

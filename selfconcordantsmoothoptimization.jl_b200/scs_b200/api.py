@@ -178,6 +178,7 @@ class Problem:
         self._h = C.c_void_p()
         self._reg_name = None
         self._host = None  # (A, y) as given: needed again only if iterate!(shuffle_batch=true) reorders the rows
+        self.row_order = None  # row permutation the device copy is currently laid out in (None: as given)
         self._storage = storage
         if A is not None and hasattr(A, "tocsc"):  # scipy.sparse (the README builds A with sprandn): CSC over the wire
             Ac = A.tocsc().astype(np.float64)
@@ -222,32 +223,41 @@ class Problem:
 
     def reorder_rows(self, order):
         """Lay the shard out in the given row order (the data loader's one-time shuffle, utils.jl:18-25): the device
-        copy is rebuilt from the host arrays, so every mini-batch becomes a contiguous row range."""
+        copy is rebuilt from the ORIGINAL host arrays (every iterate! call shuffles model.A as given, never an earlier
+        shuffle), so every mini-batch becomes a contiguous row range.  order=None restores the original order.  The
+        order in effect is recorded in `row_order`."""
         if self._host is None:
             raise UnsupportedError(K.SCS_UNSUPPORTED, "a shard generated on the device cannot be shuffled; build the "
                                                       "problem from host arrays or pass shuffle_batch=False")
         A, yv = self._host
-        order = np.asarray(order, dtype=np.int64)
-        y2 = np.ascontiguousarray(yv[order])
+        if order is None:
+            if self.row_order is None:
+                return
+            A2, y2 = A, yv
+        else:
+            order = np.asarray(order, dtype=np.int64)
+            y2 = np.ascontiguousarray(yv[order])
+            A2 = None
         K.lib().scs_problem_destroy(self._h)
         self._h = C.c_void_p()
         self._reg_name = None
         if hasattr(A, "tocsc"):  # sparse shard: permute the rows of the CSC structure, same storage choice
-            A2 = A.tocsr()[order].tocsc()
-            A2.sort_indices()
+            if A2 is None:
+                A2 = A.tocsr()[order].tocsc()
+                A2.sort_indices()
             cp = np.ascontiguousarray(A2.indptr, dtype=np.int64)
             rv = np.ascontiguousarray(A2.indices, dtype=np.int64)
             nz = np.ascontiguousarray(A2.data, dtype=np.float64)
-            self._host = (A2, y2)
             K.check(K.lib().scs_problem_create_csc(self.ctx._h, K.iptr(cp), K.iptr(rv), K.dptr(nz), 0, self.n, self.m,
                                                    K.dptr(y2), self.f.kind, self.f.param(), self.f.label_code(),
                                                    {"auto": 0, "dense": 1, "sparse": 2}[self._storage],
                                                    C.byref(self._h)))
         else:
-            A2 = np.asfortranarray(A[order])
-            self._host = (A2, y2)
+            if A2 is None:
+                A2 = np.asfortranarray(A[order])
             K.check(K.lib().scs_problem_create(self.ctx._h, K.dptr(A2), self.n, self.m, A2.shape[0], K.dptr(y2),
                                                self.f.kind, self.f.param(), self.f.label_code(), C.byref(self._h)))
+        self.row_order = None if order is None else order.copy()
         for name, val in getattr(self, "_modes", {}).items():  # kernel selections survive the rebuild
             getattr(self, name)(val)
 
@@ -401,6 +411,13 @@ class Problem:
         a, b = C.c_int(), C.c_int()
         K.check(K.lib().scs_get_gram_info(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def gram_signed(self):
+        """How the last emulated-fp64 Gram handled the weight signs: (rows compacted into the second plane set, or -1 when
+        the weights had one sign; True if the compacted rows were the negative ones)."""
+        a, b = C.c_int64(), C.c_int()
+        K.check(K.lib().scs_get_gram_signed(self._h, C.byref(a), C.byref(b)))
+        return a.value, bool(b.value)
 
     def set_stream_mode(self, mode):
         """"auto" | "two_pass" | "fused": how objective + gradient at the same x read A (once or twice)."""
@@ -565,28 +582,31 @@ def batch_plan(n, batch_size=None, slice_samples=False, shuffle_batch=False, loc
     """(row order, batch offsets) of optim_loop!'s data loader (iterate.jl:122-145, utils.jl:14-25) for n rows.
 
     MLUtils.DataLoader(batchsize, shuffle, partial=true): ceil(n/b) consecutive batches of the once-shuffled order,
-    collected ONCE before the epoch loop; slice_samples = one row per step (batch_size wins if both are given);
-    local_max_iter keeps the first min(floor(local_max_iter), max_iter) batches.  order is None when the rows stay
+    collected ONCE before the epoch loop; slice_samples steps on the FIRST row only (the loader subset is 1:iend with
+    iend = 1, see below; batch_size wins if both are given); local_max_iter keeps the first
+    min(floor(local_max_iter), max_iter) batches (and makes iterate! run a single epoch).  order is None when the rows stay
     where they are.  The shuffle itself is Julia's RNG upstream: here the permutation is an input (perm), or a
     fixed-seed numpy permutation when omitted."""
     if batch_size is not None and slice_samples:
         slice_samples = False  # iterate.jl:127-130
+    if batch_size is not None and int(batch_size) < 1:
+        raise ScsError(K.SCS_INVALID_ARG, "batch_size must be positive")
+    # max_iter and iend are computed before slice_samples sets opt.batch_size = 1 (iterate.jl:124-127 vs :136-138): with
+    # no batch_size max_iter is 1, so the loader subset 1:iend (:145) is ONE entry — for slice_samples the first row.
+    max_iter = -(-n // int(batch_size)) if batch_size is not None else 1
+    iend = max_iter
+    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
+        iend = min(int(np.floor(local_max_iter)), max_iter)
     if slice_samples:
         batch_size, shuffle_batch = 1, False
     if batch_size is None:
         batch_size, shuffle_batch = n, False
     batch_size = int(batch_size)
-    if batch_size < 1:
-        raise ScsError(K.SCS_INVALID_ARG, "batch_size must be positive")
     order = None
     if shuffle_batch:
         order = np.random.default_rng(1234).permutation(n) if perm is None else np.asarray(perm, dtype=np.int64)
         if order.shape != (n,) or not np.array_equal(np.sort(order), np.arange(n)):
             raise ScsError(K.SCS_INVALID_ARG, "perm must be a permutation of 0..n-1")
-    max_iter = -(-n // batch_size)
-    iend = max_iter
-    if local_max_iter is not None and int(np.floor(local_max_iter)) > 0:
-        iend = min(int(np.floor(local_max_iter)), max_iter)
     offsets = np.minimum(np.arange(iend + 1, dtype=np.int64) * batch_size, n)
     return order, offsets
 
@@ -603,8 +623,14 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
     several ranks the caller shards every batch over the ranks and passes this rank's local offsets (batch_offsets).
     """
     import time
+    if local_max_iter is not None:  # Options(max_epoch = local_max_iter !== nothing ? 1 : max_epoch), iterate.jl:58-70
+        max_epoch = 1
     if metrics is not None:
-        raise UnsupportedError(K.SCS_UNSUPPORTED, "user metric callbacks would have to read A on the host")
+        if device_loop:
+            raise UnsupportedError(K.SCS_UNSUPPORTED, "metrics callbacks need x on the host every epoch: use the host "
+                                                      "loop (device_loop=False)")
+        if not all(callable(fn) for fn in metrics.values()):
+            raise ScsError(K.SCS_INVALID_ARG, "metrics must map names to callables (model, x) -> value")
     offsets = None
     if batch_offsets is not None:
         offsets = np.asarray(batch_offsets, dtype=np.int64)
@@ -614,6 +640,8 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
         order, offsets = batch_plan(model.n, batch_size, slice_samples, shuffle_batch, local_max_iter, perm)
         if order is not None:
             model.reorder_rows(order)
+        elif model.row_order is not None:
+            model.reorder_rows(None)  # an earlier shuffled call left the device copy permuted
     method.set_name()  # iterate.jl:112
     if alpha is not None:
         model.L = 1 / alpha  # :113-115
@@ -674,12 +702,28 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
 
     ftests = []
     has_test = getattr(model, "_test", None) is not None
+    metric_vals = {name: [] for name in metrics} if metrics is not None else {}
+    if verbose > 0 and method.ss_type == 1 and model.L is None:  # iterate.jl:116-120
+        print("[ Info: Neither L nor α is set for the problem... Now fixing α = 0.5...")
 
-    def push(o, f, p, r, fr, v=None):  # utils.jl:106-113 (+ show_stat!'s ftest(x), utils.jl:55-57)
+    def push(o, f, p, r, fr, v=None, tag="epoch", ep=0):  # show_stat! + update_stat! (utils.jl:50-113)
+        dt = time.perf_counter() - t0
         objs.append(o), fvals.append(f), pris.append(p), rels.append(r), frels.append(fr)
-        times.append(time.perf_counter() - t0)
+        times.append(dt)
+        ft = None
         if has_test:
-            ftests.append(model.ftest(v))
+            ft = model.ftest(v)
+            ftests.append(ft)
+        for name, fn in (metrics or {}).items():  # utils.jl:80-83: metrics[name](model, x) at every recorded state
+            metric_vals[name].append(fn(model, v))
+        if verbose > 1:  # utils.jl:51-78
+            print("\n" + "=" * 30 + f"\nOptimizer:\t{method.label}")
+            print(f"{tag} = {ep}\nobj = {o}\nfval = {f}\npri_res_norm = {p}")
+            if has_test:
+                print(f"fvaltest = {ft}")
+            print(f"rel_error = {r}\nΔtime = {dt}")
+            for name in metric_vals:
+                print(f"{name}:\t{metric_vals[name][-1]}")
 
     try:
         for epoch_t in range(1, int(max_epoch) + 1):
@@ -687,13 +731,13 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
             obj = fval + reg
             rel_error = rel_err(x)
             f_rel_error = frel(obj)
-            push(obj, fval, pri_res_norm, rel_error, f_rel_error, x)
+            push(obj, fval, pri_res_norm, rel_error, f_rel_error, x, "epoch", epoch_t - 1)
             for i, (lo, hi) in enumerate(windows, start=1):  # :204
                 if epoch_t == max_epoch and i == iend:  # :219-231
                     fval, reg = objective(x)
                     obj = fval + reg
                     f_rel_error = frel(obj)
-                    push(obj, fval, pri_res_norm, rel_err(x), f_rel_error, x)
+                    push(obj, fval, pri_res_norm, rel_err(x), f_rel_error, x, "max_epoch", epoch_t)
                 if batched:
                     model.set_active_rows(lo, hi)
                 x_new, pri_res_norm = model.step(x, x_prev, epoch_t)  # :233
@@ -702,7 +746,7 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
                         fval, reg = objective(x_new)
                         obj = fval + reg
                         f_rel_error = frel(obj)
-                        push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error, x_new)
+                        push(obj, fval, pri_res_norm, rel_err(x_new), f_rel_error, x_new, "terminate_epoch", epoch_t)
                     x_prev, x = x.copy(), x_new
                     epochs += 1
                     break
@@ -713,7 +757,7 @@ def iterate(method, model, reg_name, hmu, *, metrics=None, alpha=None, batch_siz
     finally:
         if batched:
             model.set_active_rows(0, model.n)
-    return Solution(x, objs, fvals, pris, ftests, rels, frels, {}, times, epochs, model)
+    return Solution(x, objs, fvals, pris, ftests, rels, frels, metric_vals, times, epochs, model)
 
 
 def batch_shard(n, world, rank, batch_size, local_max_iter=None, perm=None):

@@ -85,3 +85,43 @@ def test_integer_gram_is_recovered_exactly_and_error_is_0p4_over_T(n, m, bits):
     err = np.max(np.abs(G - Gref) / np.outer(d, d))
     wbar = np.diag(Gref) / norms ** 2  # weighted mean of w per column
     assert err <= 2.0 / T * math.sqrt(w.max() / wbar.min()) + 1e-15, (err, 1 / T)
+
+
+@pytest.mark.parametrize("n,m,frac_neg", [(300, 5, 0.2), (500, 4, 0.9), (200, 3, 1.0)])
+def test_signed_weights_minority_compaction(n, m, frac_neg):
+    """Weights of both signs (k_residues<.., true> / k_crt): X is built from sqrt(|w|); with Xc = the rows of
+    the minority sign, sum_i w_i a_i a_i' = s_main * X'X + s_extra * Xc'Xc with (s_main, s_extra) = (+1, -2) when the
+    negative rows are the minority and (-1, +2) otherwise.  The combination is taken on the residues (chunk sums weighted by
+    the signs before the CRT), and the signed integer Gram stays inside the CRT range by the same Cauchy-Schwarz bound."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, m)) * rng.uniform(0.1, 10.0, m)
+    w = rng.uniform(0.01, 0.25, n) * np.where(rng.random(n) < frac_neg, -1.0, 1.0)
+    rows = -(-n // 128) * 128
+    norms = np.linalg.norm(A, axis=0)
+    k, T = pick(46, rows, (np.abs(A).max(axis=0) / norms).max())
+    mods = MODS[:k]
+    P = math.prod(mods)
+    scale = T / (math.sqrt(np.abs(w).max()) * norms)
+    X = np.rint((np.sqrt(np.abs(w))[:, None] * A) * scale)
+    Xi = [[int(v) for v in col] for col in X.T]
+    neg = w < 0
+    minor_neg = neg.sum() <= n - neg.sum()
+    sel = neg if minor_neg else ~neg
+    s_main, s_extra = (1, -2) if minor_neg else (-1, 2)
+    for j in range(m):
+        for l in range(j + 1):
+            exact = sum((-1 if ng else 1) * a * b for ng, a, b in zip(neg, Xi[j], Xi[l]))
+            assert abs(exact) < P // 2
+            res = []
+            for p in mods:
+                xj = [sym_res(v, p) for v in Xi[j]]
+                xl = [sym_res(v, p) for v in Xi[l]]
+                full = sym_res(sum(a * b for a, b in zip(xj, xl)), p)          # partial residue of the main SYRK
+                comp = sym_res(sum(a * b for a, b, s in zip(xj, xl, sel) if s), p)  # ... of the compacted rows
+                res.append((s_main * full + s_extra * comp) % p)
+            assert crt(res, mods) == exact
+    G = np.array([[sum((-1 if ng else 1) * a * b for ng, a, b in zip(neg, Xi[j], Xi[l])) for l in range(m)]
+                  for j in range(m)], dtype=np.float64) / np.outer(scale, scale)
+    Gref = A.T @ (w[:, None] * A)
+    d = np.sqrt(np.diag(A.T @ (np.abs(w)[:, None] * A)))
+    assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 2.0 / T * math.sqrt(np.abs(w).max() / np.abs(w).min()) + 1e-15

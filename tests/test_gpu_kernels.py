@@ -312,16 +312,106 @@ def test_gram_i8_matches_fp64(scs, n, m, bits):
         assert nmod == want or near
     with pytest.raises(scs.ScsError):
         p.set_gram_bits(44)  # planes already laid out
-    # negative weights (literal +-1 labels, GGN): not eligible -> the DMMA kernel must take over
+    # weights of both signs (literal +-1 labels, GGN: the reference's documented pair): still the int8 path — the rows of
+    # the minority sign are compacted and subtracted twice inside the CRT
     p2 = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "literal"), 0.1)
     p2.set_gram_mode("i8")
+    if bits:
+        p2.set_gram_bits(bits)
     G2 = p2.gram(x, weights="ggn")
     w2 = O.LogisticLoss(1 / n).ggn_weights(z, y)[1]
-    if np.any(w2 < 0):
-        assert p2.gram_path() == "dmma"
-    assert np.max(np.abs(G2 - A.T @ (w2[:, None] * A))) <= 1e-12 * np.max(np.abs(G2))
+    assert p2.gram_path() == "i8"
+    crow, minor_neg = p2.gram_signed()
+    nneg = int(np.sum(w2 < 0))
+    assert crow == (min(nneg, _ceil(n, 16) - nneg) if nneg else -1)  # the minority sign is the compacted one
+    G2ref = A.T @ (w2[:, None] * A)
+    d2 = np.sqrt(np.diag(A.T @ (np.abs(w2)[:, None] * A)))  # the fixed-point image is built from |w|
+    assert np.array_equal(G2, G2.T)
+    assert np.max(np.abs(G2 - G2ref) / np.outer(d2, d2)) <= tol
     p.close()
     p2.close()
+
+
+def _ceil(v, a):
+    return -(-v // a) * a
+
+
+@pytest.mark.parametrize("n,m", [(300, 40), (4096, 512), (70001, 300), (140000, 256)])
+def test_gram_i8_signed_weights(scs, n, m):
+    """Signed emulated Gram in both orientations: a few negative rows (negative rows compacted, G = X'X - 2 Xn'Xn), mostly
+    negative rows (the non-negative rows are compacted instead, G = -X'X + 2 Xp'Xp), all rows negative (least squares with a
+    negative denominator), and a mini-batch window.  Reference: A' diag(w) A in fp64 from the oracle's weights."""
+    rng = np.random.default_rng(n + m)
+    A = np.abs(synth.make_A(n, m, seed=11)) * np.where(rng.random((n, 1)) < 0.5, 1.0, 0.2)
+    x = -np.abs(synth.make_x0(m, seed=12)) * 0.4  # z < 0 on every row: yhat < 1/2
+    Lo = O.LogisticLoss(1 / n)  # literal labels
+    for frac_neg_label, want_minor_neg in ((0.15, True), (0.97, False)):
+        y = np.where(rng.random(n) < frac_neg_label, -1.0, 1.0)
+        p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "literal"), 0.1)
+        p.set_gram_mode("i8")
+        z = A @ x
+        w = Lo.ggn_weights(z, y)[1]
+        nneg = int(np.sum(w < 0))
+        assert 0 < nneg < n
+        for lo, hi in ((0, n), (n // 3 + 5, n - 7)):
+            p.set_active_rows(lo, hi)
+            G = p.gram(x, weights="ggn")
+            assert p.gram_path() == "i8"
+            ww = np.zeros(n)
+            ww[lo:hi] = w[lo:hi]
+            Gref = A.T @ (ww[:, None] * A)
+            d = np.sqrt(np.diag(A.T @ (np.abs(ww)[:, None] * A)))
+            assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 2e-12
+            crow, minor_neg = p.gram_signed()
+            if (lo, hi) == (0, n):
+                assert minor_neg == want_minor_neg == (nneg <= _ceil(n, 16) - nneg)
+                assert crow == (nneg if minor_neg else _ceil(n, 16) - nneg)
+        # the DMMA kernel on the same weights agrees (it never takes sqrt(w))
+        p.set_active_rows(0, n)
+        p.set_gram_mode("dmma")
+        Gd = p.gram(x, weights="ggn")
+        assert p.gram_path() == "dmma"
+        d = np.sqrt(np.diag(A.T @ (np.abs(w)[:, None] * A)))
+        assert np.max(np.abs(Gd - A.T @ (w[:, None] * A)) / np.outer(d, d)) <= 2e-12
+        p.close()
+    # all rows negative: least squares with a negative denominator (w = 1/p < 0 everywhere)
+    yls = rng.standard_normal(n)
+    p = scs.Problem(A, yls, x, scs.LeastSquaresLoss(-float(n)), 0.1)
+    p.set_gram_mode("i8")
+    G = p.gram(x)
+    assert p.gram_path() == "i8" and p.gram_signed()[1] is False
+    Gref = -(A.T @ A) / n
+    d = np.sqrt(np.diag(-Gref))
+    assert np.max(np.abs(G - Gref) / np.outer(d, d)) <= 2e-12
+    p.close()
+
+
+def test_gram_i8_nonfinite_weights_propagate(scs):
+    """A non-finite weight must poison the Gram like it does in fp64 arithmetic — never a silently finite matrix."""
+    n, m = 2000, 64
+    A, y, x = logistic_problem(n, m)
+    y = y.copy()
+    y[17] = np.inf  # exp(-y z) -> weight NaN on that row
+    for mode in ("literal", "consistent"):
+        p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, mode), 0.1)
+        p.set_gram_mode("i8")
+        with np.errstate(all="ignore"):
+            G = p.gram(x, weights="ggn")
+        assert not np.all(np.isfinite(G))
+        p.close()
+    # weights that are non-negative by construction take the path without any read-back: the poison flag travels on the
+    # device (k_wstat_part -> k_crt)
+    A, y, x = logistic_problem(n, m)
+    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n, "consistent"), 0.1)
+    p.set_gram_mode("i8")
+    xb = x.copy()
+    xb[3] = np.nan
+    with np.errstate(all="ignore"):
+        G = p.gram(xb, weights="ggn")
+    assert p.gram_path() == "i8" and np.all(np.isnan(G))
+    G = p.gram(x, weights="ggn")  # and the next call is clean again
+    assert np.all(np.isfinite(G))
+    p.close()
 
 
 def test_gram_i8_vs_dmma_bitwise_reproducible(scs):

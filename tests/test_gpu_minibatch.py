@@ -69,7 +69,8 @@ def test_minibatch_shuffled_and_truncated(scs, stream):
 
 
 def test_slice_samples(scs):
-    """slice_samples=true: one row per step (utils.jl:14-16).  Tiny problem: n steps per epoch."""
+    """slice_samples=true (utils.jl:14-16): the loader subset is 1:iend with iend = 1 (iterate.jl:122-145), so every
+    step! sees the FIRST row only — for ProxNSCORE a 1-row Newton system per step."""
     from test_oracle_reference_fixtures import A1, Y1, X01
     po = O.Problem(A1, Y1, X01, O.LogisticLoss(1 / 5), 1)
     pg = scs.Problem(A1, Y1, X01, scs.LogisticLoss(1 / 5), 1)
