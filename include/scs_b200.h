@@ -203,6 +203,10 @@ int scs_reg_value(scs_problem* p, const double* x, double* out);
 int scs_get_counters(scs_ctx* ctx, int64_t* launches, int reset);
 int scs_set_profiling(scs_ctx* ctx, int enable);
 int scs_get_stage_ms(scs_ctx* ctx, double* ms, int64_t* calls, int reset);
+/* Measurement aid: the int8 tensor-pipe rate of this device with the library's own 128x256x32 kind::i8 UMMA on operands
+ * resident in shared memory (no memory traffic) — the denominator bench.py uses for k_i8syrk's roofline.  burst = best of
+ * five ~20 ms launches, sustained = back-to-back launches for `seconds`.  TOP/s. */
+int scs_measure_i8_peak(scs_ctx* ctx, double seconds, double* tops_burst, double* tops_sustained);
 
 #ifdef __cplusplus
 }

@@ -879,6 +879,66 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
   }
 }
 
+// ---- int8 tensor-pipe peak (measurement aid for bench.py: the denominator of k_i8syrk's roofline) -----------------
+// One CTA per SM issues the SAME 128x256x32 kind::i8 UMMA k_i8syrk issues, back to back, on operands that never leave
+// shared memory: no TMA, no epilogue, no global traffic — what the tensor pipe sustains at the clock the power cap allows
+// with realistic (pseudo-random, non-zero) operand bits.  Commits are double-buffered so the pipe never drains.
+constexpr int kI8PeakSmem = kI8StageBytes + 1024 + 64;
+__global__ void __launch_bounds__(128, 1) k_i8peak(long long groups /* of 64 x 4 UMMAs */, uint32_t* __restrict__ sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + kI8StageBytes);
+  uint32_t* tmem_slot = (uint32_t*)(bar + 2);
+  for (int i = threadIdx.x; i < kI8StageBytes / 4; i += 128)
+    reinterpret_cast<uint32_t*>(smem)[i] = ((uint32_t)i * 2654435761u + blockIdx.x * 40503u) ^ ((uint32_t)i << 13);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // the generic-proxy fill above is read by the tensor core
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kI8TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t sa = smem_u32(smem);
+    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kI8ABytes);
+    uint32_t ph[2] = {0, 0};
+    for (long long g = 0; g < groups; ++g) {
+#pragma unroll 4
+      for (int q = 0; q < 64; ++q) {
+        const uint32_t tacc = tmem_base + (uint32_t)((q & 1) * kI8BN);
+#pragma unroll
+        for (int k = 0; k < kI8BK / 32; ++k) umma_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kI8Idesc, 1u);
+      }
+      tc_commit(&bar[g & 1]);
+      if (g > 0) {  // wait for the PREVIOUS group: at most two groups (512 UMMAs) are ever queued
+        mbar_wait(&bar[(g - 1) & 1], ph[(g - 1) & 1]);
+        ph[(g - 1) & 1] ^= 1u;
+      }
+    }
+    if (groups > 0) mbar_wait(&bar[(groups - 1) & 1], ph[(groups - 1) & 1]);
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base, v);
+    if (sink && v[threadIdx.x & 31] == 0x7fffffffu) sink[0] = v[0];  // keeps the accumulator observable
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kI8TmemCols) : "memory");
+}
+
 // ---- CRT reconstruction -----------------------------------------------------------------------------------------
 // For each lower-triangle (jc >= kc): R = CRT({sum_c partial[l][c][jc][kc] mod p_l}) in (-P/2, P/2), then
 // G[jc,kc] = G[kc,jc] = R * inv_jc * inv_kc.  One thread reconstructs 4 consecutive kc (32-bit loads of the

@@ -8,12 +8,15 @@
 //   k_tail         : damping, x+dx, scaled prox, ‖x⁺−x‖, get_reg(x⁺)
 //                                                  prox-N-SCORE.jl:92-112; prox-operators.jl:8-66;
 //                                                  prox-reg-utils.jl:84-119; regularizers.jl:4-39
-//   k_lbfgs_dir    : two_loop_recursion            prox-L-BFGS-SCORE.jl:47-68,102-106
-//   k_lbfgs_update : ∇q_new, γ, curvature guard, memory push, H0     prox-L-BFGS-SCORE.jl:148-162
+//   k_lqn_head     : smoother, ∇q, two_loop_recursion, step size (fixed / BB), damping, prox, norms, get_reg
+//                                                  prox-L-BFGS-SCORE.jl:47-68,76-146 — ONE persistent single-CTA kernel
+//   k_lqn_update   : ∇q_new, γ, curvature guard, memory push, H0     prox-L-BFGS-SCORE.jl:148-162 (the other one)
+//   k_ls_terms / k_ls_sum / k_ls_pick : Armijo line search with the trials on the device      utils.jl:27-35
 //
 // Compiled with -fmad=false: elementwise formulas round exactly like the oracle's (no silent contraction).
 #pragma once
 #include "common.cuh"
+#include "kernels_stream.cuh"  // LossParams (line-search trials)
 
 namespace scs {
 
@@ -187,14 +190,17 @@ enum {
   SC_GD = 11,     // ∇q'd  (line search)
   SC_GG = 12,     // γ'γ (BB) / scratch
   SC_DGBB = 13,   // δ'γ (BB)
-  SC_COUNT = 16
+  SC_SS = 14,     // step size the tail used (decided on the device for BB / line search)
+  SC_LSFOUND = 15,  // line search: 1 once a trial step size has passed the Armijo test
+  SC_COUNT = 16,    // copied to the host once per step
+  SC_SCRATCH = 16,  // device-only scratch behind it: a second k_pre's η² / ‖x‖² (compute_gq), the row count all-reduce
+  SC_ALLOC = 24
 };
 
 // gr, Hr at x; rhs = g + λ·gr; η² = Σ λgr_i·((1/Hr_i)·λgr_i).  g may be null (then rhs = λ·gr).
-__global__ void __launch_bounds__(kVecThreads)
-k_pre(SmoothDesc sd, double lam, const double* __restrict__ x, const double* __restrict__ g, int m,
-      double* __restrict__ gr, double* __restrict__ hr, double* __restrict__ rhs, double* __restrict__ scal) {
-  __shared__ double red[32];
+SCS_DEVINL void pre_cta(const SmoothDesc& sd, double lam, const double* __restrict__ x, const double* __restrict__ g,
+                        int m, double* __restrict__ gr, double* __restrict__ hr, double* __restrict__ rhs,
+                        double* __restrict__ scal, double* red) {
   smoother_eval_cta(sd, x, m, gr, hr, red);
   double acc = 0.0, nx = 0.0;
   for (int i = threadIdx.x; i < m; i += kVecThreads) {
@@ -209,6 +215,12 @@ k_pre(SmoothDesc sd, double lam, const double* __restrict__ x, const double* __r
     scal[SC_ETASQ] = acc;
     scal[SC_NX2] = nx;
   }
+}
+__global__ void __launch_bounds__(kVecThreads)
+k_pre(SmoothDesc sd, double lam, const double* __restrict__ x, const double* __restrict__ g, int m,
+      double* __restrict__ gr, double* __restrict__ hr, double* __restrict__ rhs, double* __restrict__ scal) {
+  __shared__ double red[32];
+  pre_cta(sd, lam, x, g, m, gr, hr, rhs, scal, red);
 }
 
 // get_reg(model, x, reg_name) by the whole CTA (regularizers.jl:4-39, prox-reg-utils.jl:101-119).
@@ -298,13 +310,13 @@ __global__ void __launch_bounds__(kVecThreads) k_prox(RegDesc rd, double ss, con
 
 // Tail of every step!: α = ss/(1+Mg·η); dx = min(1,α)·(dsign·dvec); x⁺ = prox(x+dx) or x+dx.
 // Also emits ‖δ‖², ‖x⁺−x‖², ‖x⁺−x*‖², get_reg(x⁺).  delta_out (optional) receives δ (L-BFGS s-vector).
-__global__ void __launch_bounds__(kVecThreads)
-k_tail(RegDesc rd, int use_prox, double ss, double Mg, double dsign, const double* __restrict__ x,
-       const double* __restrict__ dvec, const double* __restrict__ hr, const double* __restrict__ xstar, int m,
-       double* __restrict__ xnew, double* __restrict__ dx_out, double* __restrict__ delta_out,
-       double* __restrict__ scal) {
-  __shared__ double red[32];
-  const double eta = sqrt(scal[SC_ETASQ]);
+// eta_sq: λgr'·H⁻¹·λgr as left by pre_cta (read by the caller after a barrier).
+SCS_DEVINL void tail_cta(const RegDesc& rd, int use_prox, double ss, double Mg, double dsign, double eta_sq,
+                         const double* __restrict__ x, const double* __restrict__ dvec, const double* __restrict__ hr,
+                         const double* __restrict__ xstar, int m, double* __restrict__ xnew,
+                         double* __restrict__ dx_out, double* __restrict__ delta_out, double* __restrict__ scal,
+                         double* red) {
+  const double eta = sqrt(eta_sq);
   const double alpha = ss / (1.0 + Mg * eta);
   const double safe = alpha < 1.0 ? alpha : (alpha != alpha ? alpha : 1.0);  // min(1, α), NaN-propagating
   for (int i = threadIdx.x; i < m; i += kVecThreads) {
@@ -335,7 +347,18 @@ k_tail(RegDesc rd, int use_prox, double ss, double Mg, double dsign, const doubl
     scal[SC_DIFF2] = diff;
     scal[SC_ERR2] = err;
     scal[SC_REGNEW] = rv;
+    scal[SC_SS] = ss;
   }
+}
+// ss_dev (optional): the step size was decided on the device (line search: scal[SC_SS]) — it overrides `ss`.
+__global__ void __launch_bounds__(kVecThreads)
+k_tail(RegDesc rd, int use_prox, double ss, double Mg, double dsign, const double* __restrict__ x,
+       const double* __restrict__ dvec, const double* __restrict__ hr, const double* __restrict__ xstar, int m,
+       double* __restrict__ xnew, double* __restrict__ dx_out, double* __restrict__ delta_out,
+       double* __restrict__ scal, const double* __restrict__ ss_dev) {
+  __shared__ double red[32];
+  if (ss_dev) ss = ss_dev[0];
+  tail_cta(rd, use_prox, ss, Mg, dsign, scal[SC_ETASQ], x, dvec, hr, xstar, m, xnew, dx_out, delta_out, scal, red);
 }
 
 // ---- L-BFGS (prox-L-BFGS-SCORE.jl) ---------------------------------------------------------------
@@ -354,14 +377,14 @@ SCS_DEVINL double dot_cta(const double* __restrict__ a, const double* __restrict
 }
 
 // d = -∇q on the first iteration / empty memory, else two_loop_recursion(∇q)   (:47-68, :102-106)
-__global__ void __launch_bounds__(kVecThreads)
-k_lbfgs_dir(LbfgsMem mem, int64_t iter, const double* __restrict__ gq, int m, double* __restrict__ q,
-            double* __restrict__ d, double* __restrict__ scal) {
-  __shared__ double red[32];
-  __shared__ double alpha[64], rho[64];
+// alpha / rho: >= 64 doubles of shared memory each.  All dots are warp-shuffle + one shared-memory stage (fixed tree).
+SCS_DEVINL void lbfgs_dir_cta(const LbfgsMem& mem, int64_t iter, const double* __restrict__ gq, int m,
+                              double* __restrict__ q, double* __restrict__ d, const double* __restrict__ scal,
+                              double* red, double* alpha, double* rho) {
   const int cnt = (int)mem.state[0], head = (int)mem.state[1];
   if (iter == 1 || cnt == 0) {
     for (int i = threadIdx.x; i < m; i += kVecThreads) d[i] = -gq[i];
+    __syncthreads();
     return;
   }
   for (int i = threadIdx.x; i < m; i += kVecThreads) q[i] = gq[i];
@@ -393,23 +416,67 @@ k_lbfgs_dir(LbfgsMem mem, int64_t iter, const double* __restrict__ gq, int m, do
     __syncthreads();
   }
   for (int i = threadIdx.x; i < m; i += kVecThreads) d[i] = -q[i];
+  __syncthreads();
+}
+// BB: δ = x − x_prev, γ = gq − gq_prev;  scal[SC_GG] = γ'γ, scal[SC_DGBB] = δ'γ   (utils.jl:43-48).  Returns
+// (γ'γ)/(δ'γ) — used *as* the step size — to every thread.
+SCS_DEVINL double bb_cta(const double* __restrict__ x, const double* __restrict__ xp, const double* __restrict__ gq,
+                         const double* __restrict__ gqp, int m, double* __restrict__ scal, double* red) {
+  double gg = 0.0, dg = 0.0;
+  for (int i = threadIdx.x; i < m; i += kVecThreads) {
+    const double de = x[i] - xp[i], ga = gq[i] - gqp[i];
+    gg += ga * ga;
+    dg += de * ga;
+  }
+  gg = block_sum<kVecThreads>(gg, red);
+  dg = block_sum<kVecThreads>(dg, red);
+  if (threadIdx.x == 0) {
+    scal[SC_GG] = gg;
+    scal[SC_DGBB] = dg;
+  }
+  return gg / dg;
+}
+
+// ---- the persistent ProxLQNSCORE kernels: one launch before the gradient pass, one after ------------------------------
+// k_lqn_head = everything step! does at x before it needs ∇f(x⁺) (prox-L-BFGS-SCORE.jl:76-146): smoother gradient / Hessian
+// diagonal, ∇q (or the one carried over from the previous step's k_lqn_update), two-loop recursion over the device-
+// resident memory, the step size (fixed, or the BB estimate — decided here, no host round trip), damping, x + dx, scaled
+// prox, ‖δ‖, get_reg(x⁺).  mode: 0 = ss given, 1 = BB from (x, x_prev, ∇q, ∇q_prev), 2 = direction only (a line search
+// follows; the tail is k_tail with the step size it leaves in scal[SC_SS]).
+__global__ void __launch_bounds__(kVecThreads)
+k_lqn_head(SmoothDesc sd, RegDesc rd, LbfgsMem mem, double lam, double Mg, double ss, int mode, int use_prox,
+           int64_t iter, const double* __restrict__ x, const double* __restrict__ xprev,
+           const double* __restrict__ g /* A'r at x, or null: gq already holds ∇q(x) */, int m,
+           double* __restrict__ gr, double* __restrict__ hr, double* __restrict__ gq,
+           const double* __restrict__ gqprev, double* __restrict__ q, double* __restrict__ d,
+           const double* __restrict__ xstar, double* __restrict__ xnew, double* __restrict__ dx_out,
+           double* __restrict__ delta_out, double* __restrict__ scal) {
+  __shared__ double red[32];
+  __shared__ double alpha[64], rho[64];
+  pre_cta(sd, lam, x, g, m, gr, hr, g ? gq : (double*)nullptr, scal, red);
+  __syncthreads();
+  lbfgs_dir_cta(mem, iter, gq, m, q, d, scal, red, alpha, rho);
+  if (mode == 2) return;
+  if (mode == 1) ss = bb_cta(x, xprev, gq, gqprev, m, scal, red);
+  tail_cta(rd, use_prox, ss, Mg, 1.0, scal[SC_ETASQ], x, d, hr, xstar, m, xnew, dx_out, delta_out, scal, red);
 }
 
 // ∇q_new = g_new + λ·hμ.grad(x⁺);  γ = ∇q_new − ∇q;  push (δ, γ) if δ'γ > 1e-10;  H0 = γ'δ/γ'γ   (:148-162)
-// gq is overwritten with ∇q_new (it is next iteration's ∇q: same x, same bits).
-__global__ void __launch_bounds__(kVecThreads)
-k_lbfgs_update(SmoothDesc sd, double lam, LbfgsMem mem, const double* __restrict__ xnew,
-               const double* __restrict__ gnew, const double* __restrict__ delta, int m,
-               double* __restrict__ gq, double* __restrict__ gamma, double* __restrict__ gr_tmp,
-               double* __restrict__ hr_tmp, double* __restrict__ scal) {
-  __shared__ double red[32];
+// gq is overwritten with ∇q_new (it is next iteration's ∇q: same x, same bits); gqprev (optional) receives the old ∇q.
+SCS_DEVINL void lbfgs_update_cta(const SmoothDesc& sd, double lam, const LbfgsMem& mem, const double* __restrict__ xnew,
+                                 const double* __restrict__ gnew, const double* __restrict__ delta, int m,
+                                 double* __restrict__ gq, double* __restrict__ gqprev, double* __restrict__ gamma,
+                                 double* __restrict__ gr_tmp, double* __restrict__ hr_tmp, double* __restrict__ scal,
+                                 double* red) {
   smoother_eval_cta(sd, xnew, m, gr_tmp, hr_tmp, red);
   double dg = 0.0, gg = 0.0;
   for (int i = threadIdx.x; i < m; i += kVecThreads) {
     const double qn = gnew[i] + lam * gr_tmp[i];
-    const double gm = qn - gq[i];
+    const double qo = gq[i];
+    const double gm = qn - qo;
     gamma[i] = gm;
     gq[i] = qn;
+    if (gqprev) gqprev[i] = qo;
     dg += delta[i] * gm;
     gg += gm * gm;
   }
@@ -445,6 +512,130 @@ k_lbfgs_update(SmoothDesc sd, double lam, LbfgsMem mem, const double* __restrict
     scal[SC_PUSHED] = push ? 1.0 : 0.0;
   }
 }
+// k_lqn_update = what step! does after the gradient pass at x⁺ (:148-162).  On one GPU it also folds the per-cluster
+// partial gradients and per-CTA loss sums of k_fused_grad itself (gpart != null; the same fixed order as k_colsum /
+// k_sum_partials, so both routes give the same bits): an iteration is then k_lqn_head, k_fused_grad, k_lqn_update.
+__global__ void __launch_bounds__(kVecThreads)
+k_lqn_update(SmoothDesc sd, double lam, LbfgsMem mem, const double* __restrict__ xnew, double* __restrict__ gl /* [g ‖ loss] */,
+             const double* __restrict__ gpart, int64_t nparts, const double* __restrict__ losspart, int64_t nloss,
+             const double* __restrict__ delta, int m, double* __restrict__ gq, double* __restrict__ gqprev,
+             double* __restrict__ gamma, double* __restrict__ gr_tmp, double* __restrict__ hr_tmp,
+             double* __restrict__ scal) {
+  __shared__ double red[32];
+  if (gpart) {
+    for (int j = threadIdx.x; j < m; j += kVecThreads) {  // k_colsum's order: 8 interleaved slices, then their sum
+      double sl[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int64_t b = 0; b < nparts; b += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (b + q < nparts) sl[q] += gpart[(b + q) * m + j];
+      }
+      double t = sl[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) t += sl[q];
+      gl[j] = t;
+    }
+    double sacc = 0.0;
+    for (int64_t i = threadIdx.x; i < nloss; i += kVecThreads) sacc += losspart[i];
+    sacc = block_sum<kVecThreads>(sacc, red);
+    if (threadIdx.x == 0) gl[m] = sacc;
+    __syncthreads();
+  }
+  lbfgs_update_cta(sd, lam, mem, xnew, gl, delta, m, gq, gqprev, gamma, gr_tmp, hr_tmp, scal, red);
+}
+
+// ---- Armijo line search on the device (utils.jl:27-35) -----------------------------------------------------------
+// The reference evaluates f(x + α d) for α = 1, 1/2, 1/4, ... — one pass over A per trial.  Here ONE pass gives
+// zd = A d; with z = A x (left by the pass at x) every trial is z + α zd: a batch of kLsTrials step sizes costs one sweep
+// over two row vectors.  k_ls_terms: part[b*8 + k] = Σ_{rows of block b} term(z_i + α_k (dsign zd_i)), α_k = alpha0 2^-k.
+constexpr int kLsTrials = 8;
+constexpr int kLsRowsPerBlock = 4096;
+enum { LS_FX = 0, LS_GD = 1, LS_COUNT = 2 };
+SCS_DEVINL double loss_term_only(const LossParams& lp, double z, double y) {
+  if (lp.kind == 0) return log(1.0 + exp(-y * z));
+  const double d = z - y;
+  return d * d;
+}
+__global__ void __launch_bounds__(256)
+k_ls_terms(const double* __restrict__ z, const double* __restrict__ zd, const double* __restrict__ y, int64_t nproc,
+           int64_t row_lo, int64_t row_hi, LossParams lp, double dsign, double alpha0, const double* __restrict__ scal,
+           double* __restrict__ part) {
+  __shared__ double red[32];
+  if (scal[SC_LSFOUND] != 0.0) return;  // an earlier batch already accepted a step size
+  double acc[kLsTrials];
+#pragma unroll
+  for (int k = 0; k < kLsTrials; ++k) acc[k] = 0.0;
+  const int64_t b0 = (int64_t)blockIdx.x * kLsRowsPerBlock;
+  for (int64_t i = b0 + threadIdx.x; i < b0 + kLsRowsPerBlock && i < nproc; i += 256) {
+    if (i < row_lo || i >= row_hi) continue;  // padding, or rows of another mini-batch
+    const double zi = z[i], di = dsign * zd[i], yi = y[i];
+    double a = alpha0;
+#pragma unroll
+    for (int k = 0; k < kLsTrials; ++k) {
+      acc[k] += loss_term_only(lp, zi + a * di, yi);
+      a *= 0.5;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kLsTrials; ++k) {
+    const double t = block_sum<256>(acc[k], red);
+    if (threadIdx.x == 0) part[(int64_t)blockIdx.x * kLsTrials + k] = t;
+  }
+}
+// sums[k] = Σ_b part[b*8 + k] in fixed order (several ranks: this is what gets all-reduced)
+__global__ void __launch_bounds__(kVecThreads)
+k_ls_sum(const double* __restrict__ part, int64_t nblk, const double* __restrict__ scal, double* __restrict__ sums) {
+  __shared__ double red[32];
+  if (scal[SC_LSFOUND] != 0.0) return;
+  for (int k = 0; k < kLsTrials; ++k) {
+    double s = 0.0;
+    for (int64_t b = threadIdx.x; b < nblk; b += kVecThreads) s += part[b * kLsTrials + k];
+    s = block_sum<kVecThreads>(s, red);
+    if (threadIdx.x == 0) sums[k] = s;
+  }
+}
+// The Armijo test over the batch, in order: accept the first α_k with  !(f(x + α_k d) > f(x) + 1e-4 α_k <∇q, d>).
+// first != 0: also evaluates f(x) = fscale(loss sum at x) + get_reg(x) and <∇q, d> once (the reference recomputes the same
+// values every trial) into ls[].  loss_kind / loss_p: fval = p*S (logistic) or 0.5*S/p (least squares).
+__global__ void __launch_bounds__(kVecThreads)
+k_ls_pick(RegDesc rd, int loss_kind, double loss_p, const double* __restrict__ x, const double* __restrict__ dvec,
+          double dsign, const double* __restrict__ gq, int m, double alpha0, int first,
+          const double* __restrict__ loss_sum_x, const double* __restrict__ sums, double* __restrict__ trial,
+          double* __restrict__ ls, double* __restrict__ scal) {
+  __shared__ double red[32];
+  if (scal[SC_LSFOUND] != 0.0) return;
+  if (first) {
+    const double S = loss_sum_x[0];
+    const double fv = loss_kind == 0 ? loss_p * S : 0.5 * S / loss_p;
+    const double rv = reg_value_cta(rd, x, m, red);
+    const double gd = dsign * dot_cta(gq, dvec, m, red);
+    if (threadIdx.x == 0) {
+      ls[LS_FX] = fv + rv;
+      ls[LS_GD] = gd;
+      scal[SC_REGX] = rv;
+      scal[SC_GD] = dsign * gd;
+    }
+    __syncthreads();
+  }
+  const double fx = ls[LS_FX], gd = ls[LS_GD];
+  double a = alpha0;
+  for (int k = 0; k < kLsTrials; ++k) {
+    for (int i = threadIdx.x; i < m; i += kVecThreads) trial[i] = x[i] + (dsign * a) * dvec[i];
+    __syncthreads();
+    const double rv = reg_value_cta(rd, trial, m, red);
+    const double S = sums[k];
+    const double ft = (loss_kind == 0 ? loss_p * S : 0.5 * S / loss_p) + rv;
+    if (!(ft > fx + 1e-4 * a * gd)) {  // NaN accepts, like the reference's `while f(..) > ..`
+      if (threadIdx.x == 0) {
+        scal[SC_SS] = a;
+        scal[SC_LSFOUND] = 1.0;
+      }
+      return;
+    }
+    a *= 0.5;
+    __syncthreads();
+  }
+}
 
 // ---- small helpers ----------------------------------------------------------------------------
 // out = a + alpha*b
@@ -460,23 +651,11 @@ __global__ void __launch_bounds__(kVecThreads) k_dot(const double* __restrict__ 
   const double s = dot_cta(a, b, m, red);
   if (threadIdx.x == 0) scal[slot] = s;
 }
-// BB: δ = x − x_prev, γ = gq − gq_prev;  scal[SC_GG] = γ'γ, scal[SC_DGBB] = δ'γ   (utils.jl:43-48)
 __global__ void __launch_bounds__(kVecThreads)
 k_bb(const double* __restrict__ x, const double* __restrict__ xp, const double* __restrict__ gq,
      const double* __restrict__ gqp, int m, double* __restrict__ scal) {
   __shared__ double red[32];
-  double gg = 0.0, dg = 0.0;
-  for (int i = threadIdx.x; i < m; i += kVecThreads) {
-    const double de = x[i] - xp[i], ga = gq[i] - gqp[i];
-    gg += ga * ga;
-    dg += de * ga;
-  }
-  gg = block_sum<kVecThreads>(gg, red);
-  dg = block_sum<kVecThreads>(dg, red);
-  if (threadIdx.x == 0) {
-    scal[SC_GG] = gg;
-    scal[SC_DGBB] = dg;
-  }
+  bb_cta(x, xp, gq, gqp, m, scal, red);
 }
 
 }  // namespace scs

@@ -238,10 +238,12 @@ struct scs_problem {
   int stream_mode = 0;       // 0 auto, 1 two passes (k_forward + k_adjoint), 2 fused whenever the shape is supported
   int last_stream_path = 0;  // 1 two passes, 2 fused
   bool fu_ready = false, fu_failed = false;
-  int fu_cluster = 1, fu_clusters = 0;
+  int fu_cluster = 1, fu_clusters = 0, fu_last_ncl = 0;
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
-  double* d_u = nullptr;  // row vector of the GGN wide branch (ldd doubles, allocated on first use)
+  double* d_u = nullptr;  // row vector of the GGN wide branch / A d of the line search (ldd doubles, allocated on first use)
+  double* d_lspart = nullptr;  // line search: per-block trial sums | 8 sums | f(x), <∇q,d>
+  int64_t lspart_cap = 0;
   // sparse shard (kernels_sparse.cuh): CSR + CSC copies, no dense A
   bool sparse = false;
   int64_t nnz = 0;
@@ -358,10 +360,10 @@ static int set_window(scs_problem* p, int64_t lo, int64_t hi, int64_t rows_globa
   p->win_rows_global = rows_global >= 0 ? rows_global : hi - lo;
   if (p->ctx->world > 1 && rows_global < 0) {  // the GGN wide-branch test needs the global batch size
     const double v = (double)(hi - lo);
-    CU_TRY(cudaMemcpyAsync(p->d_scal + SC_COUNT - 1, &v, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
-    SCS_TRY(allreduce(p->ctx, p->d_scal + SC_COUNT - 1, 1));
+    CU_TRY(cudaMemcpyAsync(p->d_scal + SC_ALLOC - 1, &v, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    SCS_TRY(allreduce(p->ctx, p->d_scal + SC_ALLOC - 1, 1));
     double tot = 0;
-    CU_TRY(cudaMemcpyAsync(&tot, p->d_scal + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+    CU_TRY(cudaMemcpyAsync(&tot, p->d_scal + SC_ALLOC - 1, sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
     CU_TRY(cudaStreamSynchronize(p->ctx->stream));
     p->win_rows_global = (int64_t)(tot + 0.5);
   }
@@ -442,7 +444,9 @@ static bool fused_wanted(scs_problem* p) {
 }
 
 // one read of A: z, r, w, the local loss sum in d_gl[m] and the local A'r in d_gl[0..m)
-static int run_fused(scs_problem* p, const double* dx, int wk) {
+// reduce = false: the per-cluster partial gradients / per-CTA loss sums are left for the caller's kernel to fold
+// (k_lqn_update on one GPU); p->fu_last_ncl = clusters launched.
+static int run_fused(scs_problem* p, const double* dx, int wk, bool reduce = true) {
   scs_ctx* c = p->ctx;
   SCS_TRY(fused_setup(p));
   StageTimer t(c, ST_FUSED);
@@ -482,8 +486,11 @@ static int run_fused(scs_problem* p, const double* dx, int wk) {
   }
   c->launches += 1;
   if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_fused_grad launch: ") + cudaGetErrorString(le));
-  LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_fupart, (int64_t)ncl, (int)p->m, p->d_gl);
-  LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_fuloss, (int64_t)ncl * p->fu_cluster, p->d_gl + p->m);
+  p->fu_last_ncl = ncl;
+  if (reduce) {
+    LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_fupart, (int64_t)ncl, (int)p->m, p->d_gl);
+    LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_fuloss, (int64_t)ncl * p->fu_cluster, p->d_gl + p->m);
+  }
   p->last_stream_path = 2;
   return SCS_OK;
 }
@@ -1321,6 +1328,52 @@ extern "C" int scs_get_stage_ms(scs_ctx* c, double* ms8, int64_t* calls8, int re
   return SCS_OK;
 }
 
+// int8 tensor-pipe peak of this device, measured with the library's own UMMA (k_i8peak): burst = best of 5 launches of
+// ~20 ms, sustained = back-to-back launches for `seconds`.  TOP/s = 2 * 128 * 256 * 32 ops per UMMA.
+extern "C" int scs_measure_i8_peak(scs_ctx* c, double seconds, double* tops_burst, double* tops_sustained) {
+  if (!c) return fail(SCS_INVALID_ARG, "ctx is NULL");
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaFuncSetAttribute(k_i8peak, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8PeakSmem));
+  uint32_t* sink = nullptr;
+  CU_TRY(cudaMalloc((void**)&sink, sizeof(uint32_t)));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  const double ops_per_group = 64.0 * (kI8BK / 32) * 2.0 * kI8BM * kI8BN * 32.0 * c->num_sms;
+  const long long groups = 700;  // ~20 ms per launch at ~2.5 POP/s
+  auto launch = [&]() {
+    k_i8peak<<<c->num_sms, 128, kI8PeakSmem, c->stream>>>(groups, sink);
+    c->launches += 1;
+  };
+  launch();  // warm-up
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  CU_TRY(cudaGetLastError());
+  double best = 0.0;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0, c->stream);
+    launch();
+    cudaEventRecord(e1, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::max(best, ops_per_group * groups / (ms * 1e-3) / 1e12);
+  }
+  const int reps = std::max(3, (int)(seconds * best * 1e12 / (ops_per_group * groups)));
+  cudaEventRecord(e0, c->stream);
+  for (int r = 0; r < reps; ++r) launch();
+  cudaEventRecord(e1, c->stream);
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (tops_burst) *tops_burst = best;
+  if (tops_sustained) *tops_sustained = ops_per_group * groups * reps / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  CU_TRY(cudaGetLastError());
+  return SCS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // exported: problem lifetime
 // ------------------------------------------------------------------------------------------------
@@ -1359,7 +1412,7 @@ static int problem_alloc(scs_ctx* ctx, int64_t n_local, int64_t m, int loss_kind
                      &p->d_gq,    &p->d_gqprev, &p->d_gamma, &p->d_q,   &p->d_t1, &p->d_t2, &p->d_xstar,
                      &p->d_trial, &p->d_gnewton};
   for (auto v : vecs) SCS_TRY(dalloc(v, p->mp));
-  SCS_TRY(dalloc(&p->d_scal, SC_COUNT));
+  SCS_TRY(dalloc(&p->d_scal, SC_ALLOC));
   CU_TRY(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 8) * sizeof(double)));
   p->fwd_blocks = dense ? (p->ldd + kFwdRows - 1) / kFwdRows : (n_local + kSpFwdRows - 1) / kSpFwdRows;
   p->win_lo = 0;
@@ -1384,7 +1437,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
@@ -1926,14 +1979,38 @@ extern "C" int scs_objective(scs_problem* p, const double* x, double* fval, doub
 static int compute_gq(scs_problem* p, XRef v, double lam, double* dout) {
   SCS_TRY(ensure_grad(p, v, SCS_WEIGHTS_NEWTON));
   StageTimer t(p->ctx, ST_VEC);
-  LAUNCH(p->ctx, k_pre, 1, kVecThreads, 0, p->sm, lam, v.d, p->d_gl, (int)p->m, p->d_t1, p->d_t2, dout, p->d_scal + SC_GG);
+  LAUNCH(p->ctx, k_pre, 1, kVecThreads, 0, p->sm, lam, v.d, p->d_gl, (int)p->m, p->d_t1, p->d_t2, dout, p->d_scal + SC_SCRATCH);
+  return SCS_OK;
+}
+
+// z_out = A v on the rows of the active window (no loss pieces): the line search's A d
+static int run_matvec(scs_problem* p, const double* dv, double* zout) {
+  scs_ctx* c = p->ctx;
+  StageTimer t(c, ST_FWD);
+  LossParams lp = p->loss;
+  lp.kind = 2;  // z only
+  lp.weight_kind = 0;
+  if (p->sparse) {
+    const int64_t blocks = (p->n + kSpFwdRows - 1) / kSpFwdRows;
+    LAUNCH(c, k_sp_forward, (unsigned)blocks, kSpFwdThreads, 0, (const int64_t*)p->d_rowptr, (const int*)p->d_colidx,
+           (const double*)p->d_vals, p->n, p->win_lo, p->win_hi, dv, (const double*)p->dy, lp, zout, (double*)nullptr,
+           (double*)nullptr, p->d_losspart);
+    return SCS_OK;
+  }
+  const int64_t nproc = p->ahi - p->alo;
+  const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
+  if (blocks > 0)
+    LAUNCH(c, k_forward<8>, (unsigned)blocks, kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc, p->win_lo - p->alo,
+           p->win_hi - p->alo, (int)p->m, dv, p->dy + p->alo, lp, zout + p->alo, (double*)nullptr, (double*)nullptr,
+           p->d_losspart);
   return SCS_OK;
 }
 
 // Armijo backtracking of utils.jl:27-35 with f = nonsmooth objective, grad = smoothed ∇q.  f(x) and <∇q,d> are
-// evaluated once (the reference recomputes the same values every trial).
-static int linesearch_device(scs_problem* p, XRef x, const double* d_dir, double dsign, const double* d_gqx,
-                             double* ss_out) {
+// evaluated once (the reference recomputes the same values every trial).  The host loop below is only used for the
+// quadform loss (not a sum over rows); everything else goes through linesearch_device.
+static int linesearch_hostloop(scs_problem* p, XRef x, const double* d_dir, double dsign, const double* d_gqx,
+                               double* ss_out) {
   scs_ctx* c = p->ctx;
   SCS_TRY(ensure_loss(p, x, p->fwd_id == x.id ? p->fwd_wk : SCS_WEIGHTS_NEWTON));
   LAUNCH(c, k_reg, 1, kVecThreads, 0, p->reg, x.d, (int)p->m, p->d_scal + SC_REGX);
@@ -1957,7 +2034,60 @@ static int linesearch_device(scs_problem* p, XRef x, const double* d_dir, double
     if (!(ft > fx + 1e-4 * alpha * gd)) break;
     alpha = 0.5 * alpha;
   }
+  const double a = alpha;
+  CU_TRY(cudaMemcpyAsync(p->d_scal + SC_SS, &a, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   *ss_out = alpha;
+  return SCS_OK;
+}
+
+// The same search with the trials on the device: ONE pass over A gives zd = A d; with z = A x from the pass at x every
+// trial point is z + α zd, so a batch of 8 step sizes (α, α/2, ..., α/128) costs one sweep over two row vectors
+// (k_ls_terms), one 8-double all-reduce when the rows are sharded, and one single-CTA kernel that adds get_reg(x + α d)
+// and applies the Armijo test in order (k_ls_pick).  The accepted α stays on the device (scal[SC_SS], read by k_tail);
+// the host looks at the "found" flag once per batch instead of synchronising on every trial.
+static int linesearch_device(scs_problem* p, XRef x, const double* d_dir, double dsign, const double* d_gqx,
+                             double* ss_out) {
+  scs_ctx* c = p->ctx;
+  if (p->loss.kind == SCS_LOSS_QUADFORM) return linesearch_hostloop(p, x, d_dir, dsign, d_gqx, ss_out);
+  const int m = (int)p->m;
+  // z = A x and the loss sum at x: whatever pass produced them is cached by id
+  SCS_TRY(ensure_loss(p, x, p->fwd_id == x.id ? p->fwd_wk : SCS_WEIGHTS_NEWTON));
+  if (!p->d_u) SCS_TRY(dalloc(&p->d_u, p->ldd));
+  const int64_t r0 = p->sparse ? 0 : p->alo, nproc = p->sparse ? p->n : p->ahi - p->alo;
+  const int64_t nblk = std::max<int64_t>(1, (nproc + kLsRowsPerBlock - 1) / kLsRowsPerBlock);
+  if (!p->d_lspart || p->lspart_cap < nblk) {
+    dfree(p->d_lspart);
+    p->d_lspart = nullptr;
+    SCS_TRY(dalloc(&p->d_lspart, (size_t)nblk * kLsTrials + kLsTrials + LS_COUNT));
+    p->lspart_cap = nblk;
+  }
+  double* sums = p->d_lspart + (size_t)p->lspart_cap * kLsTrials;
+  double* ls = sums + kLsTrials;
+  SCS_TRY(run_matvec(p, d_dir, p->d_u));
+  CU_TRY(cudaMemsetAsync(p->d_scal + SC_LSFOUND, 0, sizeof(double), c->stream));
+  double alpha0 = 1.0;
+  for (int batch = 0; batch < 140; ++batch) {  // 140 * 8 halvings: past the point where α underflows to 0 (accepts)
+    StageTimer t(c, ST_VEC);
+    LAUNCH(c, k_ls_terms, (unsigned)nblk, 256, 0, (const double*)(p->dz + r0), (const double*)(p->d_u + r0),
+           (const double*)(p->dy + r0), nproc, p->win_lo - r0, p->win_hi - r0, p->loss, dsign, alpha0,
+           (const double*)p->d_scal, p->d_lspart);
+    LAUNCH(c, k_ls_sum, 1, kVecThreads, 0, (const double*)p->d_lspart, nblk, (const double*)p->d_scal, sums);
+    SCS_TRY(allreduce(c, sums, kLsTrials));  // every rank queues the same sequence (the flag is replicated)
+    LAUNCH(c, k_ls_pick, 1, kVecThreads, 0, p->reg, p->loss.kind, p->loss.p, (const double*)x.d, d_dir, dsign, d_gqx, m,
+           alpha0, batch == 0 ? 1 : 0, (const double*)(p->d_gl + p->m), (const double*)sums, p->d_trial, ls, p->d_scal);
+    CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal + SC_SS, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (p->h_scal[1] != 0.0) {
+      *ss_out = p->h_scal[0];
+      return SCS_OK;
+    }
+    alpha0 = std::ldexp(alpha0, -kLsTrials);
+    if (alpha0 == 0.0) break;
+  }
+  // α underflowed: f(x + 0 d) > f(x) is false, the reference accepts α = 0
+  const double zero = 0.0;
+  CU_TRY(cudaMemcpyAsync(p->d_scal + SC_SS, &zero, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  *ss_out = 0.0;
   return SCS_OK;
 }
 
@@ -2012,65 +2142,83 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
     }
     StageTimer t(c, ST_VEC);
     LAUNCH(c, k_tail, 1, kVecThreads, 0, p->reg, p->use_prox, ss, Mg, -1.0, x.d, p->d_sol, p->d_hr, d_xstar, m, xnew,
-           p->d_dx, (double*)nullptr, p->d_scal);
+           p->d_dx, (double*)nullptr, p->d_scal, (const double*)nullptr);
     return SCS_OK;
   }
 
-  // ---- ProxLQNSCORE ----
+  // ---- ProxLQNSCORE: two persistent single-CTA kernels around the gradient pass --------------------------------
+  //   k_lqn_head   : gr, Hr, ∇q (or the one carried over), two-loop recursion, step size, damping, prox, norms, get_reg
+  //   k_fused_grad : f(x⁺), ∇f(x⁺) in one read of A
+  //   k_lqn_update : (partial sums of the pass,) ∇q(x⁺), γ, curvature guard, memory push, H0
   if (!(type1 || p->ss_type == 2 || p->ss_type == 3 || !p->has_L))
     return fail(SCS_INVALID_ARG, "Please, choose ss_type in [1, 2, 3].");
-  if (p->gq_id == x.id) {
-    StageTimer t(c, ST_VEC);  // ∇q carried over from the previous step; only gr, Hr, η are needed
-    LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, (const double*)nullptr, m, p->d_gr, p->d_hr,
-           (double*)nullptr, p->d_scal);
-  } else {
-    SCS_TRY(ensure_grad(p, x, SCS_WEIGHTS_NEWTON));
-    StageTimer t(c, ST_VEC);
-    LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_gq, p->d_scal);
-    p->gq_id = x.id;
-  }
-  {
-    StageTimer t(c, ST_VEC);
-    LbfgsMem mem{p->d_S, p->d_Y, p->d_state, p->lbfgs_cap};
-    LAUNCH(c, k_lbfgs_dir, 1, kVecThreads, 0, mem, iter, p->d_gq, m, p->d_q, p->d_d, p->d_scal);
-  }
+  const bool carried = p->gq_id == x.id;  // ∇q(x) is the ∇q_new of the previous step (same x, same bits)
+  if (!carried) SCS_TRY(ensure_grad(p, x, SCS_WEIGHTS_NEWTON));
+  int mode = 0;  // 0: ss known here, 1: BB on the device, 2: direction only (line search follows)
   if (!type1) {
     if (p->ss_type == 2 || !p->has_L) {  // prox-L-BFGS-SCORE.jl:112-119 (ss_type 3 without L lands here too)
       if (iter == 1) {
         ss = 1.0;
       } else {
+        mode = 1;
         if (p->gqprev_id != xprev.id) {
-          // ∇q(x_prev) is not the one carried over: recompute it (keeps the current ∇q and forward cache intact
-          // only by id, so restore them afterwards)
+          // ∇q(x_prev) is not the one kept from the previous step: recompute it.  That evicts the cached pass at x, so
+          // a ∇q(x) that has not been formed yet is formed first.
+          if (!carried) {
+            StageTimer t(c, ST_VEC);
+            LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, p->d_gl, m, p->d_gr, p->d_hr, p->d_gq, p->d_scal);
+            p->gq_id = x.id;
+          }
           SCS_TRY(compute_gq(p, xprev, lam, p->d_gqprev));
           p->gqprev_id = xprev.id;
         }
-        LAUNCH(c, k_bb, 1, kVecThreads, 0, x.d, xprev.d, p->d_gq, p->d_gqprev, m, p->d_scal);
-        CU_TRY(cudaMemcpyAsync(p->h_scal, p->d_scal + SC_GG, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        ss = p->h_scal[0] / p->h_scal[1];  // (γ·γ)/(δ'γ), used *as* the step size
-        // k_pre's η² lives in SC_ETASQ and is untouched by compute_gq (it wrote to SC_GG..)
       }
     } else {
-      SCS_TRY(linesearch_device(p, x, p->d_d, 1.0, p->d_gq, &ss));
+      mode = 2;
     }
   }
   {
     StageTimer t(c, ST_VEC);
+    const bool have_gq = p->gq_id == x.id;
+    LbfgsMem mem{p->d_S, p->d_Y, p->d_state, p->lbfgs_cap};
+    LAUNCH(c, k_lqn_head, 1, kVecThreads, 0, p->sm, p->reg, mem, lam, Mg, ss, mode, p->use_prox ? 1 : 0, iter,
+           (const double*)x.d, (const double*)xprev.d, have_gq ? (const double*)nullptr : (const double*)p->d_gl, m,
+           p->d_gr, p->d_hr, p->d_gq, (const double*)p->d_gqprev, p->d_q, p->d_d, d_xstar, xnew, p->d_dx, p->d_delta,
+           p->d_scal);
+    p->gq_id = x.id;
+  }
+  if (mode == 2) {
+    SCS_TRY(linesearch_device(p, x, p->d_d, 1.0, p->d_gq, &ss));
+    StageTimer t(c, ST_VEC);
     LAUNCH(c, k_tail, 1, kVecThreads, 0, p->reg, p->use_prox, ss, Mg, 1.0, x.d, p->d_d, p->d_hr, d_xstar, m, xnew,
-           p->d_dx, p->d_delta, p->d_scal);
+           p->d_dx, p->d_delta, p->d_scal, (const double*)(p->d_scal + SC_SS));
   }
   // second gradient at x⁺ (prox-L-BFGS-SCORE.jl:148-150); it is next iteration's ∇q, and its loss value is next
   // epoch's objective, so neither is recomputed
   XRef xn{xnew, xnew_id};
-  SCS_TRY(ensure_grad(p, xn, SCS_WEIGHTS_NEWTON));
+  const bool fold = c->world == 1 && fused_wanted(p) && !(p->fwd_id == xn.id);
+  int folded = 0;
+  if (fold) {
+    int rc = run_fused(p, xn.d, SCS_WEIGHTS_NEWTON, /*reduce=*/false);
+    if (rc == SCS_OK) {
+      p->fwd_id = xn.id;
+      p->fwd_wk = SCS_WEIGHTS_NEWTON;
+      p->loss_reduced = true;
+      p->grad_id = xn.id;
+      folded = 1;
+    } else if (!(rc == SCS_UNSUPPORTED && p->stream_mode == 0)) {
+      return rc;
+    }
+  }
+  if (!folded) SCS_TRY(ensure_grad(p, xn, SCS_WEIGHTS_NEWTON));
   {
     StageTimer t(c, ST_VEC);
-    CU_TRY(cudaMemcpyAsync(p->d_gqprev, p->d_gq, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    p->gqprev_id = x.id;
     LbfgsMem mem{p->d_S, p->d_Y, p->d_state, p->lbfgs_cap};
-    LAUNCH(c, k_lbfgs_update, 1, kVecThreads, 0, p->sm, lam, mem, xnew, p->d_gl, p->d_delta, m, p->d_gq, p->d_gamma,
-           p->d_t1, p->d_t2, p->d_scal);
+    LAUNCH(c, k_lqn_update, 1, kVecThreads, 0, p->sm, lam, mem, (const double*)xnew, p->d_gl,
+           folded ? (const double*)p->d_fupart : (const double*)nullptr, (int64_t)p->fu_last_ncl,
+           (const double*)p->d_fuloss, (int64_t)p->fu_last_ncl * p->fu_cluster, (const double*)p->d_delta, m, p->d_gq,
+           p->d_gqprev, p->d_gamma, p->d_t1, p->d_t2, p->d_scal);
+    p->gqprev_id = x.id;
     p->gq_id = xnew_id;
   }
   return SCS_OK;

@@ -1,8 +1,10 @@
 # SCSB200.jl — Julia shim that routes the per-iteration hot path of SelfConcordantSmoothOptimization.jl
 # (ProxNSCORE / ProxGGNSCORE / ProxLQNSCORE) to libscs_b200.so through `ccall`.
 #
-# Drop-in: `Problem(A, y, x0, f, λ; ...)`, `iterate!(method, problem, reg_name, hμ; ...)` and the `Solution` fields
-# keep their reference meaning.  The only change a user makes is to pass one of the built-in loss objects
+# Drop-in: `Problem(A, y, x0, f, λ; ...)`, `iterate!(method, problem, reg_name, hμ; ...)` — the SAME function, this module
+# adds a more specific method for `model::Problem` — and the `Solution` fields keep their reference meaning (histories,
+# `fvaltest` from `Atest/ytest`, `metricvals`, `times`, verbose printing through the reference's own `show_stat!`).
+# The only change a user makes is to pass one of the built-in loss objects
 # (`LogisticLoss`, `LeastSquaresLoss`, `QuadFormLoss`; all `<: Function`, so `Problem`'s `f::Function` signature,
 # src/problems.jl:65, accepts them).  An arbitrary closure `f` — which only ForwardDiff could differentiate — is
 # rejected with an error instead of silently running on the CPU.
@@ -18,7 +20,7 @@ import SelfConcordantSmoothOptimization: iterate!, ProximalMethod, ProxNSCORE, P
     LogExpSmootherIndBox, OsBaSmootherL1L2, OsBaSmootherGL, bounds_sanity_check
 using LinearAlgebra, Dates, Random, SparseArrays
 
-export LogisticLoss, LeastSquaresLoss, QuadFormLoss, GPUContext, gpu_iterate!
+export LogisticLoss, LeastSquaresLoss, QuadFormLoss, GPUContext, gpu_iterate!, iterate!
 
 const LIB = get(ENV, "SCS_B200_LIB", joinpath(@__DIR__, "..", "libscs_b200.so"))
 
@@ -172,77 +174,147 @@ set_active_rows!(p::GPUProblem, lo::Integer, hi::Integer) =
     check(ccall((:scs_set_active_rows, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), p.h, lo, hi))
 
 # The data loader of optim_loop! (iterate.jl:122-145, utils.jl:14-25): row order after the one-time shuffle and the
-# batch offsets.  MLUtils.DataLoader(batchsize, shuffle, partial=true) gives ceil(n/b) consecutive batches.
+# batch offsets.  MLUtils.DataLoader(batchsize, shuffle, partial=true) gives ceil(n/b) consecutive batches.  max_iter and
+# iend are fixed BEFORE slice_samples sets batch_size = 1 (:124-127 vs :136-138): without a batch_size max_iter stays 1, so
+# the loader subset 1:iend (:145) is ONE entry — for slice_samples that is the first row only.
 function batch_plan(n::Integer; batch_size=nothing, slice_samples=false, shuffle_batch=true, local_max_iter=nothing)
     batch_size !== nothing && slice_samples && (slice_samples = false)
+    max_iter = batch_size !== nothing ? cld(n, batch_size) : 1
+    iend = (local_max_iter !== nothing && Int(floor(local_max_iter)) > 0) ? min(Int(floor(local_max_iter)), max_iter) : max_iter
     slice_samples && ((batch_size, shuffle_batch) = (1, false))
     batch_size === nothing && ((batch_size, shuffle_batch) = (n, false))
     order = shuffle_batch ? Random.shuffle(1:n) : nothing
-    max_iter = cld(n, batch_size)
-    iend = (local_max_iter !== nothing && Int(floor(local_max_iter)) > 0) ? min(Int(floor(local_max_iter)), max_iter) : max_iter
     offsets = [min(i * batch_size, n) for i in 0:iend]
     return order, offsets
 end
 
-# optim_loop! (iterate.jl:100-266) with the two hot call sites routed to the GPU; histories, stopping rules and the
-# Solution are the reference's.  Mini-batches: the rows are uploaded once in the loader's (shuffled) order, so every
-# batch is a contiguous row range of the resident matrix; the objective is always taken over all rows (:189).
-function gpu_iterate!(method::ProximalMethod, model, reg_name, hμ; ctx::GPUContext=GPUContext(0), α=nothing,
-                      batch_size=nothing, slice_samples=false, shuffle_batch=true, local_max_iter=nothing,
-                      max_epoch=1000, x_tol=1e-10, f_tol=1e-10, smoother_bounds=nothing, kwargs...)
-    SelfConcordantSmoothOptimization.set_name!(method, [])
-    α !== nothing && (model.L = 1 / α)
+const BuiltinLoss = Union{LogisticLoss,LeastSquaresLoss,QuadFormLoss}
+
+# ---- the drop-in entry point -------------------------------------------------------------------------------------
+# `iterate!(method, problem, reg_name, hμ; ...)` ITSELF (iterate.jl:56-76): this method is more specific than the
+# reference's (`model::Problem` vs `model::SCMOModel`), so after `using .SCSB200` every `iterate!` on a `Problem` lands here.
+# A built-in loss goes to the GPU.  Anything else (an arbitrary closure f, which only ForwardDiff can differentiate) is
+# REJECTED — never run on the CPU silently; `backend=:cpu` asks for the reference's own CPU path explicitly.
+function iterate!(method::ProximalMethod, model::Problem, reg_name, hμ; backend::Symbol=:gpu, ctx=nothing,
+                  smoother_bounds=nothing, kwargs...)
+    if backend == :cpu
+        return invoke(iterate!, Tuple{ProximalMethod,SelfConcordantSmoothOptimization.SCMOModel,Any,Any}, method, model,
+                      reg_name, hμ; kwargs...)
+    end
+    model.f isa BuiltinLoss ||
+        Base.error("scs_b200: arbitrary user f (ForwardDiff-only path) is not supported on the GPU; pass LogisticLoss / " *
+                   "LeastSquaresLoss / QuadFormLoss, or call iterate!(...; backend=:cpu) for the reference CPU path")
+    return gpu_iterate!(method, model, reg_name, hμ; ctx=(ctx === nothing ? GPUContext(0) : ctx),
+                        smoother_bounds=smoother_bounds, kwargs...)
+end
+
+# optim_loop! (iterate.jl:100-266) with the two hot call sites routed to the GPU.  Everything that is host bookkeeping
+# upstream stays the reference's own code: Options, show_stat! (verbose printing, ftest, metrics: utils.jl:50-104) and
+# update_stat! (histories: utils.jl:106-113) are called as they are.  Mini-batches: the rows are uploaded once in the
+# loader's (shuffled) order, so every batch is a contiguous row range of the resident matrix; the objective is always
+# taken over all rows (:189).
+function gpu_iterate!(method::ProximalMethod, model, reg_name, hμ; ctx::GPUContext=GPUContext(0),
+                      metrics=nothing, α=nothing, batch_size=nothing, slice_samples=false, shuffle_batch=true,
+                      max_epoch=1000, comm_rounds=100, local_max_iter=nothing, x_tol=1e-10, f_tol=1e-10, verbose=1,
+                      smoother_bounds=nothing)
+    SCS = SelfConcordantSmoothOptimization
+    opt = SCS.Options(metrics=metrics, α=α, batch_size=batch_size, slice_samples=slice_samples,
+                      shuffle_batch=shuffle_batch, max_epoch=(local_max_iter !== nothing ? 1 : max_epoch),
+                      comm_rounds=comm_rounds, local_max_iter=local_max_iter, x_tol=x_tol, f_tol=f_tol, verbose=verbose)
+    max_epoch = opt.max_epoch                                    # iterate.jl:58-70
+    implemented_algs = []
+    SCS.set_name!(method, implemented_algs)                      # :112
+    α !== nothing && (model.L = 1 / α)                           # :113-115
+    if method.name in implemented_algs && method.ss_type == 1 && model.L === nothing && verbose > 0
+        @info "Neither L nor α is set for the problem... Now fixing α = 0.5..."   # :116-120
+    end
     n = size(model.A, 1)
+    if batch_size !== nothing && slice_samples
+        @info "Cannot use both batch_size and slice_samples=true...\nNow setting slice_samples=false..."  # :128-131
+    end
     batched = batch_size !== nothing || slice_samples
     order, offsets = batch_plan(n; batch_size=batch_size, slice_samples=slice_samples, shuffle_batch=shuffle_batch,
                                 local_max_iter=local_max_iter)
-    if order !== nothing   # one-time shuffle: upload the rows in loader order
-        model = deepcopy(model); model.A = model.A[order, :]; model.y = model.y[order]
+    opt.max_iter = batch_size !== nothing ? cld(n, batch_size) : 1
+    dev_model = model
+    if order !== nothing   # one-time shuffle: upload the rows in loader order (the caller's model is left untouched)
+        dev_model = deepcopy(model); dev_model.A = model.A[order, :]; dev_model.y = model.y[order]
     end
     windows = batched ? [(offsets[i], offsets[i+1]) for i in 1:length(offsets)-1] : [(0, n)]
     iend = length(windows)
-    p = GPUProblem(ctx, model)
+    p = GPUProblem(ctx, dev_model)
     configure!(p, method, model, reg_name, hμ; smoother_bounds=smoother_bounds)
     objective(v) = (batched && set_active_rows!(p, 0, n); gpu_objective(p, v))
-    objs, fvals, pris, rels, frels, times = [], [], [], [], [], []
+    # held-out data (iterate.jl:169-176): a second resident shard; ftest(x) = model.f(Atest, ytest, x)
+    test_model = all(x -> x !== nothing, (model.Atest, model.ytest))
+    if xor(model.Atest === nothing, model.ytest === nothing)
+        @info "Both input (Atest) and target (ytest) data are required for testing the model, but only one of these has been provided.\nWill skip testing..."
+    end
+    ptest = nothing
+    if test_model
+        tm = deepcopy(model); tm.A = model.Atest; tm.y = model.ytest
+        ptest = GPUProblem(ctx, tm)
+        configure!(ptest, method, model, reg_name, hμ; smoother_bounds=smoother_bounds)
+    end
+    ftest = test_model ? (v -> gpu_objective(ptest, v)[1]) : (v -> nothing)
+    fvals, pri_res_norms, fvaltests, objs, rel_errors, f_rel_errors, times = [], [], [], [], [], [], []
+    metric_vals = Dict()
+    if metrics !== nothing
+        for name in keys(metrics); metric_vals[name] = []; end
+    end
+    epochs = 0
     x_star = model.x
     fs, rs = objective(x_star)
-    obj_star = fs + rs
-    x = copy(model.x0); x_prev = deepcopy(x)
-    check(ccall((:scs_method_init, LIB), Cint, (Ptr{Cvoid},), p.h))
-    rel_err(v) = reg_name == "gl" ? sum(abs2, x_star - v) / length(v) : max(norm(v - x_star) / max(norm(x_star), 1), x_tol)
-    frel(o) = max(norm(o - obj_star) / norm(obj_star), f_tol)
-    pri = nothing; epochs = 0; f_rel_error = 0.0
+    obj_star = fs + rs                                           # :179
+    x = model.x0; x_prev = deepcopy(x)
+    pri_res_norm = nothing
+    l_split = "="^30 * "\n"
+    check(ccall((:scs_method_init, LIB), Cint, (Ptr{Cvoid},), p.h))   # init!(method, x) :183
+    rel_err(v) = reg_name == "gl" ? SCS.mean_square_error(x_star, v) : max(norm(v - x_star) / max.(norm(x_star), 1), x_tol)
+    frel(o) = max((norm(o - obj_star)) / norm(obj_star), f_tol)
     t0 = now()
-    push_stat!(o, f, r, fr) = (push!(objs, o); push!(fvals, f); push!(pris, pri); push!(rels, r); push!(frels, fr);
-                               push!(times, (now() - t0).value / 1000))
     for epoch_t in 1:max_epoch
-        f, r = objective(x); obj = f + r
+        Δtime = (now() - t0).value / 1000
+        fval, reg = objective(x); obj = fval + reg               # :189-190
+        rel_error = rel_err(x)
         f_rel_error = frel(obj)
-        push_stat!(obj, f, rel_err(x), f_rel_error)
-        for (i, (lo, hi)) in enumerate(windows)
-            if epoch_t == max_epoch && i == iend
-                f, r = objective(x); obj = f + r; f_rel_error = frel(obj)
-                push_stat!(obj, f, rel_err(x), f_rel_error)
+        SCS.show_stat!(opt, model, method, x, test_model, ftest, fvaltests, epoch_t - 1, obj, fval, pri_res_norm, rel_error, Δtime, metric_vals, l_split)
+        SCS.update_stat!(objs, obj, fvals, fval, pri_res_norms, pri_res_norm, rel_errors, rel_error, f_rel_errors, f_rel_error, times, Δtime)
+        for (i, (lo, hi)) in enumerate(windows)                  # :204
+            if verbose > 2
+                (i in [1, iend]) || (i % 100 == 0) ? print("\n[$i/$iend]") : print("#")
+            end
+            if epoch_t == max_epoch && i == iend                 # :219-231
+                Δtime = (now() - t0).value / 1000
+                fval, reg = objective(x); obj = fval + reg
+                rel_error = rel_err(x)
+                SCS.show_stat!(opt, model, method, x, test_model, ftest, fvaltests, epoch_t, obj, fval, pri_res_norm, rel_error, Δtime, metric_vals, l_split; is_max_epoch=true)
+                f_rel_error = frel(obj)
+                SCS.update_stat!(objs, obj, fvals, fval, pri_res_norms, pri_res_norm, rel_errors, rel_error, f_rel_errors, f_rel_error, times, Δtime)
             end
             batched && set_active_rows!(p, lo, hi)
-            x_new, pri = gpu_step(p, x, x_prev, epoch_t)
-            if norm(x_new - x) < x_tol * max(norm(x), 1) || f_rel_error ≤ f_tol || pri < x_tol
-                if epoch_t != max_epoch
-                    f, r = objective(x_new); obj = f + r; f_rel_error = frel(obj)
-                    push_stat!(obj, f, rel_err(x_new), f_rel_error)
+            x_new, pri_res_norm = gpu_step(p, x, x_prev, epoch_t)   # :233
+            if norm(x_new - x) < x_tol * max.(norm(x), 1) || f_rel_error ≤ f_tol || pri_res_norm < x_tol
+                if epoch_t != max_epoch                          # :235-247
+                    Δtime = (now() - t0).value / 1000
+                    fval, reg = objective(x_new); obj = fval + reg
+                    rel_error = rel_err(x_new)
+                    SCS.show_stat!(opt, model, method, x_new, test_model, ftest, fvaltests, epoch_t, obj, fval, pri_res_norm, rel_error, Δtime, metric_vals, l_split; is_terminate_epoch=true)
+                    f_rel_error = frel(obj)
+                    SCS.update_stat!(objs, obj, fvals, fval, pri_res_norms, pri_res_norm, rel_errors, rel_error, f_rel_errors, f_rel_error, times, Δtime)
                 end
                 x_prev = deepcopy(x); x = x_new; epochs += 1
                 break
             end
             x_prev = deepcopy(x); x = x_new
         end
-        if norm(x - x_prev) < x_tol * max(norm(x_prev), 1) || f_rel_error ≤ f_tol || pri < x_tol
+        if norm(x - x_prev) < x_tol * max.(norm(x_prev), 1) || f_rel_error ≤ f_tol || pri_res_norm < x_tol   # :257
             break
         end
         epochs += 1
+        verbose > 2 && print("\n" * l_split)
     end
-    return Solution(x, objs, fvals, pris, [], rels, frels, Dict(), times, epochs, model)
+    return Solution(x, objs, fvals, pri_res_norms, fvaltests, rel_errors, f_rel_errors, metric_vals, times, epochs, model)
 end
 
 end # module

@@ -65,6 +65,12 @@ class Context:
         K.check(K.lib().scs_get_stage_ms(self._h, K.dptr(ms), K.iptr(calls), int(reset)))
         return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(K.STAGES)}
 
+    def measure_i8_peak(self, seconds=1.5):
+        """(burst, sustained) int8 tensor-pipe TOP/s of this device with the library's own UMMA loop (no memory traffic)."""
+        a, b = C.c_double(), C.c_double()
+        K.check(K.lib().scs_measure_i8_peak(self._h, float(seconds), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def linear_solve(self, M, b):
         """(H + λHr) \\ ∇q on the device: Cholesky, pivoted-LU fallback.  Returns (d, used_fallback)."""
         M = np.asfortranarray(np.asarray(M, dtype=np.float64))

@@ -17,13 +17,32 @@ import scs_b200 as S  # noqa: E402
 from oracle import scs_oracle as O  # noqa: E402
 
 
+def run_checks(ctx, rank, world, quick=False):
+    """Multi-rank parity against the full-batch oracle; torch.distributed must be initialised (NCCL).  Returns the worst
+    relative error seen.  quick: two configurations only (bench.py --selftest)."""
+    worst = 0.0
+    names = ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1") if quick else ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1", "c4_ls_ggn_gl", "c5_ls_n_indbox")
+    worst = _full_batch_checks(ctx, rank, world, names)
+    if not quick:
+        worst = max(worst, _minibatch_checks(ctx, rank, world))
+    return worst
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = S.context_from_env()
+    worst = run_checks(ctx, rank, world)
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIRANK_OK world={world} worst_rel_err={worst:.3e}")
+    dist.destroy_process_group()
+
+
+def _full_batch_checks(ctx, rank, world, names):
     worst = 0.0
-    for name in ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1", "c4_ls_ggn_gl", "c5_ls_n_indbox"):
+    for name in names:
         A, y, x0 = cases.data(name)
         mo, modelo, reg, ho, kw = cases.build(name, O)
         so = O.iterate(mo, modelo, reg, ho, **kw)
@@ -63,6 +82,11 @@ def main():
         dist.all_gather(lst, t)
         assert all(torch.equal(lst[0], u) for u in lst), name
         model.close()
+    return worst
+
+
+def _minibatch_checks(ctx, rank, world):
+    worst = 0.0
     # ---- mini-batches across ranks: every (shuffled) batch is split over the ranks, each rank uploads its slices
     # batch after batch and steps through its local offsets; held-out rows are sharded the same way
     name = "c3_logreg_lqn_l1"
@@ -89,10 +113,7 @@ def main():
             assert ex <= 1e-10 and eo <= 1e-10 and et <= 1e-10, (mname, dl, rank, ex, eo, et)
             worst = max(worst, ex, eo, et)
             model.close()
-    dist.barrier()
-    if rank == 0:
-        print(f"MULTIRANK_OK world={world} worst_rel_err={worst:.3e}")
-    dist.destroy_process_group()
+    return worst
 
 
 if __name__ == "__main__":
