@@ -481,6 +481,8 @@ def main():
         last = fv + rv
     barrier()
     t_e2e = time.perf_counter() - t0
+    gram_path = model.gram_path()  # of the timed steps (the parity check below switches kernels)
+    gram_info = model.gram_info()
     parity = None
     if wl["method"] != "lqn" and not args.no_parity and args.gram != "dmma":
         parity = parity_at_scale(S, method, model, reg, hmu, alpha, x0, rank)
@@ -512,11 +514,10 @@ def main():
         a_ms, a_calls = stages["adjoint"]
         nl = n_local
         roof = None
-        gram_path = model.gram_path()
         gram_equiv = None
         if g_calls and gram_path == "i8":
             # emulated-fp64 Gram: k_i8syrk runs NMOD int8 SYRKs; algorithmic int8 ops = NMOD * n*m*(m+1)
-            nmod, kept_bits = model.gram_info()
+            nmod, kept_bits = gram_info
             ops = nmod * float(nl) * m * (m + 1)
             ach = ops / (g_ms / g_calls * 1e-3) / 1e12
             if i8_peak is not None:

@@ -945,10 +945,13 @@ __global__ void __launch_bounds__(128, 1) k_i8peak(long long groups /* of 64 x 4
 // int8 partial residues).
 __global__ void __launch_bounds__(256)
 k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ inv, const double* __restrict__ wstat,
-      int expect_nonneg, double* __restrict__ G) {
+      int expect_nonneg, double* __restrict__ G, int jc_lo, int jc_hi, double* __restrict__ Gpack) {
+  // rows [jc_lo, jc_hi) of the lower triangle (several ranks: the Gram is reconstructed slab by slab so that the
+  // all-reduce of one slab overlaps the CRT of the next).  Gpack != null: write the packed upper triangle
+  // Gpack[jc (jc+1)/2 + kc] = G[kc, jc] (kc <= jc) instead of the two full triangles — half the all-reduce volume.
   const int kc0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-  const int jc = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (jc >= pl.m || kc0 >= pl.m || kc0 > jc) return;
+  const int jc = jc_lo + blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (jc >= jc_hi || kc0 >= pl.m || kc0 > jc) return;
   // a non-finite weight poisons every entry of the fp64 Gram; so does (defensively) a negative weight on a path that
   // was planned for non-negative ones — never a silently wrong matrix
   const bool poisoned = wstat[WS_BAD] != 0.0 || (expect_nonneg && wstat[WS_NNEG] != 0.0);
@@ -998,8 +1001,35 @@ k_crt(const int8_t* __restrict__ partial, I8Plan pl, const double* __restrict__ 
     if (neg) d = -d;
     double g = (d * ij) * inv[kc];
     if (poisoned) g = __longlong_as_double(0x7ff8000000000000LL);
-    G[(int64_t)kc * pl.m + jc] = g;
-    G[(int64_t)jc * pl.m + kc] = g;
+    if (Gpack) {
+      Gpack[(int64_t)jc * (jc + 1) / 2 + kc] = g;
+    } else {
+      G[(int64_t)kc * pl.m + jc] = g;
+      G[(int64_t)jc * pl.m + kc] = g;
+    }
+  }
+}
+
+// G (m x m, both triangles) from the packed upper triangle P[jc (jc+1)/2 + kc] (kc <= jc).  32 x 32 tiles, grid.x enumerates
+// the tiles with tile-row (kc) <= tile-column (jc); reads and both writes are coalesced (transposed half through smem).
+__global__ void __launch_bounds__(256) k_unpack_upper(const double* __restrict__ P, int m, double* __restrict__ G) {
+  __shared__ double tile[32][33];
+  int tj, tk;  // jc tile >= kc tile
+  tri_decode(blockIdx.x, tj, tk);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int jc = tj * 32 + cc, kc = tk * 32 + tx;
+    double v = 0.0;
+    if (jc < m && kc <= jc) {
+      v = P[(int64_t)jc * (jc + 1) / 2 + kc];
+      G[(int64_t)jc * m + kc] = v;  // (row kc, column jc)
+    }
+    tile[cc][tx] = v;
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int kc = tk * 32 + rr, jc = tj * 32 + tx;
+    if (jc < m && kc < jc) G[(int64_t)kc * m + jc] = tile[tx][rr];  // (row jc, column kc)
   }
 }
 

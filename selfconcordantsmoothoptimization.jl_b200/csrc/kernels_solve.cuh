@@ -195,7 +195,7 @@ SCS_DEVINL void load_tile_T(double* dst, const double* __restrict__ M, int64_t l
 // right-hand side below the block: b_i -= sum_c L[i, k0+c] y_c (128 rows each).  128 threads.
 // tile0: first triangular tile index handled by CTA 0 (the look-ahead sequence passes 1: the diagonal tile right below
 // the panel belongs to k_chol_diag).
-__global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0, int ntiles,
+__global__ void __launch_bounds__(128, 3) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0, int ntiles,
                                                      double* __restrict__ bvec, const double* __restrict__ yvec,
                                                      int tile0) {
   extern __shared__ double tile_sh[];
@@ -243,28 +243,28 @@ __global__ void __launch_bounds__(128) k_syrk_update(double* __restrict__ M, int
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
-  // issue the read half of the read-modify-write before the MMAs so its latency hides behind them
-  double old[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
-        old[i][j][h] = (row < m && col < m && row >= col) ? M[(int64_t)col * ld + row] : 0.0;
-      }
   double acc[4][4][2] = {};
   tile_mma_64(As, Bs, wm, wn, g, t, acc);
+  // read-modify-write in four batches of eight independent loads: the batch latency hides behind the other resident
+  // CTAs (keeping all 32 old values in registers across the MMAs cost a third CTA per SM: 230 -> ~170 registers)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    double old[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
-        if (row < m && col < m && row >= col) M[(int64_t)col * ld + row] = old[i][j][h] - acc[i][j][h];
+        old[j][h] = (row < m && col < m && row >= col) ? __ldcg(M + (int64_t)col * ld + row) : 0.0;
       }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = r0 + wm + 8 * i + g, col = c0 + wn + 8 * j + 2 * t + h;
+        if (row < m && col < m && row >= col) M[(int64_t)col * ld + row] = old[j][h] - acc[i][j][h];
+      }
+  }
 }
 
 // ---- look-ahead sequence (default): k_chol_diag -> k_chol_trsm on the main stream, k_syrk_update on a second one ------

@@ -67,6 +67,7 @@ struct scs_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // trailing updates of the look-ahead Cholesky (run_solve)
   cudaEvent_t ev_trsm[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+  cudaEvent_t ev_slab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // slab-pipelined Gram all-reduce
   int solve_mode = 0;  // 0 = look-ahead sequence, 1 = k_panel / k_syrk_update sequence (SCS_SOLVE_LEGACY=1)
   bool solve_attr_set = false;
   int p2p_capacity = -1;
@@ -90,8 +91,9 @@ struct scs_ctx {
 struct StageTimer {  // records an event pair around a stage when profiling is on
   scs_ctx* c;
   int stage;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  StageTimer(scs_ctx* c_, int s) : c(c_), stage(s) {
+  StageTimer(scs_ctx* c_, int s, cudaStream_t stream = nullptr) : c(c_), stage(s), st(stream ? stream : c_->stream) {
     if (!c->profiling) return;
     auto get = [&]() {
       cudaEvent_t e;
@@ -105,11 +107,11 @@ struct StageTimer {  // records an event pair around a stage when profiling is o
     };
     a = get();
     b = get();
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, st);
   }
   ~StageTimer() {
     if (!c->profiling) return;
-    cudaEventRecord(b, c->stream);
+    cudaEventRecord(b, st);
     c->pending.push_back({stage, a, b});
   }
 };
@@ -141,10 +143,11 @@ static int ctx_sync(scs_ctx* c) {
   return SCS_OK;
 }
 
-static int allreduce(scs_ctx* c, double* buf, size_t count) {
+static int allreduce(scs_ctx* c, double* buf, size_t count, cudaStream_t stream = nullptr) {
   if (c->world <= 1) return SCS_OK;
-  StageTimer t(c, ST_COMM);
-  int r = g_nccl.AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, c->comm, c->stream);
+  if (!stream) stream = c->stream;
+  StageTimer t(c, ST_COMM, stream);
+  int r = g_nccl.AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, c->comm, stream);
   if (r != 0) return fail(SCS_NCCL_ERROR, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
   return SCS_OK;
 }
@@ -218,6 +221,7 @@ struct scs_problem {
   int8_t *d_planes = nullptr, *d_i8partial = nullptr;
   // signed weights: compacted planes of the minority-sign rows (i8_setup_signed), per-block statistics
   int8_t* d_cplanes = nullptr;
+  double* d_Gpack = nullptr;  // several ranks: packed upper triangle of the Gram, what the all-reduce moves
   int64_t ldc = 0, i8_ccount = 0;
   int64_t* d_negbase = nullptr;
   double* d_wpart = nullptr;
@@ -336,7 +340,7 @@ static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
   return SCS_OK;
 }
 
-static int allreduce(scs_ctx* c, double* buf, size_t count);
+static int allreduce(scs_ctx* c, double* buf, size_t count, cudaStream_t stream);
 // Select the rows that take part in the following passes.  Everything cached for the previous window is dropped.
 static int set_window(scs_problem* p, int64_t lo, int64_t hi, int64_t rows_global = -1) {
   if (lo < 0 || hi < lo || hi > p->n) return fail(SCS_INVALID_ARG, "row window outside the shard");
@@ -361,7 +365,7 @@ static int set_window(scs_problem* p, int64_t lo, int64_t hi, int64_t rows_globa
   if (p->ctx->world > 1 && rows_global < 0) {  // the GGN wide-branch test needs the global batch size
     const double v = (double)(hi - lo);
     CU_TRY(cudaMemcpyAsync(p->d_scal + SC_ALLOC - 1, &v, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
-    SCS_TRY(allreduce(p->ctx, p->d_scal + SC_ALLOC - 1, 1));
+    SCS_TRY(allreduce(p->ctx, p->d_scal + SC_ALLOC - 1, 1, nullptr));
     double tot = 0;
     CU_TRY(cudaMemcpyAsync(&tot, p->d_scal + SC_ALLOC - 1, sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
     CU_TRY(cudaStreamSynchronize(p->ctx->stream));
@@ -911,12 +915,43 @@ static int run_gram_i8(scs_problem* p, int* done) {
     SCS_TRY(i8_launch_syrk(p, p->xmap, p->xmap_b, pl));
     if (cpl.nchunks > 0) SCS_TRY(i8_launch_syrk(p, p->cmap, p->cmap_b, cpl));
   }
-  {
+  if (c->world <= 1) {
     StageTimer t(c, ST_GRAMFIN);
     LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv,
-           (const double*)p->d_wstat, nonneg ? 1 : 0, p->d_G);
+           (const double*)p->d_wstat, nonneg ? 1 : 0, p->d_G, 0, m, (double*)nullptr);
+    *done = 1;
+    return SCS_OK;
   }
-  *done = 1;
+  // Several ranks: the exchange step.  Only the packed upper triangle travels (half the bytes of the square), and it
+  // travels slab by slab: the CRT of slab s+1 runs on the main stream while NCCL reduces slab s on the second stream.
+  // Slab boundaries split the packed triangle into equal byte counts (rows ~ sqrt).
+  if (!p->d_Gpack) SCS_TRY(dalloc(&p->d_Gpack, (size_t)m * (m + 1) / 2));
+  const int nslab = m >= 2048 ? 4 : 1;
+  int j0 = 0;
+  for (int sidx = 0; sidx < nslab; ++sidx) {
+    int j1 = sidx == nslab - 1 ? m : (int)std::floor(m * std::sqrt((sidx + 1.0) / nslab));
+    j1 = std::min(m, std::max(j0 + 4, j1 / 4 * 4));
+    if (sidx == nslab - 1) j1 = m;
+    {
+      StageTimer t(c, ST_GRAMFIN);
+      LAUNCH(c, k_crt, dim3((j1 + 255) / 256, (j1 - j0 + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv,
+             (const double*)p->d_wstat, nonneg ? 1 : 0, p->d_G, j0, j1, p->d_Gpack);
+    }
+    CU_TRY(cudaEventRecord(c->ev_slab[sidx], c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream2, c->ev_slab[sidx], 0));
+    const size_t off0 = (size_t)j0 * (j0 + 1) / 2, off1 = (size_t)j1 * (j1 + 1) / 2;
+    SCS_TRY(allreduce(c, p->d_Gpack + off0, off1 - off0, c->stream2));
+    j0 = j1;
+    if (j0 >= m) break;
+  }
+  CU_TRY(cudaEventRecord(c->ev_slab[4], c->stream2));
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_slab[4], 0));
+  {
+    StageTimer t(c, ST_GRAMFIN);
+    const int t32 = (m + 31) / 32;
+    LAUNCH(c, k_unpack_upper, t32 * (t32 + 1) / 2, 256, 0, (const double*)p->d_Gpack, m, p->d_G);
+  }
+  *done = 2;  // all-reduced already
   return SCS_OK;
 }
 
@@ -964,7 +999,7 @@ static int run_gram(scs_problem* p, XRef x) {
               c->rank, g_err.c_str());
     if (done) {
       p->last_gram_path = 2;
-      SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
+      if (done == 1) SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
       return SCS_OK;
     }
   }
@@ -1248,6 +1283,7 @@ extern "C" int scs_ctx_create(int device, int rank, int world, const void* id128
     CU_TRY(cudaEventCreateWithFlags(&c->ev_trsm[i], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_upd[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < 5; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming));
   if (const char* e = getenv("SCS_SOLVE_LEGACY")) c->solve_mode = atoi(e) ? 1 : 0;
   CU_TRY(cudaMalloc((void**)&c->d_flag, sizeof(double)));
   void* fn = nullptr;
@@ -1291,6 +1327,8 @@ extern "C" int scs_ctx_destroy(scs_ctx* c) {
     if (c->ev_trsm[i]) cudaEventDestroy(c->ev_trsm[i]);
     if (c->ev_upd[i]) cudaEventDestroy(c->ev_upd[i]);
   }
+  for (int i = 0; i < 5; ++i)
+    if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
   delete c;
   return SCS_OK;
 }
@@ -1437,7 +1475,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_Gpack, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);

@@ -163,8 +163,9 @@ def test_error_behaviour(scs):
     with pytest.raises(scs.ScsError, match="bounds"):  # prox-reg-utils.jl:154
         p.C_set = (-1.0, 1.0)
         scs.iterate(scs.ProxNSCORE(), p, "indbox", scs.PHuberSmootherIndBox(np.zeros(3), np.ones(3), 1.0), verbose=0)
-    with pytest.raises(scs.UnsupportedError):  # metric callbacks would need A on the host
-        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), metrics={"acc": lambda m, x: 0.0}, verbose=0)
+    with pytest.raises(scs.UnsupportedError):  # metric callbacks need x on the host every epoch: host loop only
+        scs.iterate(scs.ProxNSCORE(), p, "l1", scs.PHuberSmootherL1L2(1.0), metrics={"acc": lambda m, x: 0.0}, verbose=0,
+                    device_loop=True)
     with pytest.raises(scs.ScsError):  # a mini-batch window must stay inside the shard
         p.set_active_rows(0, A.shape[0] + 1)
     p.close()
