@@ -467,7 +467,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         for (int sg = 0; sg < segs; ++sg) {
           const unsigned long long point = (unsigned long long)(st * segs + sg);
-          if (point > 0) {
+          if (point > 0 && progress != nullptr) {  // progress == nullptr: free-running (tuning aid SCS_I8_NOLOCK=1)
             atomicAdd(progress, 1ULL);
             if (in_step) {
               const unsigned long long want = point * ncta;
@@ -715,7 +715,8 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
       const unsigned long long ncta = gridDim.x;
       bool in_step = true;
       const int h = crank >> 1;  // which 64 of the 128 rows of its B half this CTA fetches
-      const uint16_t bmask = (uint16_t)((1u << q) | (1u << (q + 2)));  // the two CTAs that hold half q
+      // the CTAs that hold half q: ranks q and q + 2 (cluster of 4 = two pairs), or just this one (cluster of 2 = one pair)
+      const uint16_t bmask = (uint16_t)(((1u << q) | (1u << (q + 2))) & kMaskAll);
       for (int64_t st = 0; st < steps; ++st) {
         const int64_t u = cid + st * ncl;
         const bool valid = u < pl.units;
@@ -726,7 +727,7 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
         const int64_t kb1 = kb0 + pl.chunk_kblocks < pl.kblocks ? kb0 + pl.chunk_kblocks : pl.kblocks;
         for (int sg = 0; sg < segs; ++sg) {
           const unsigned long long point = (unsigned long long)(st * segs + sg);
-          if (point > 0) {
+          if (point > 0 && progress != nullptr) {  // progress == nullptr: free-running (tuning aid SCS_I8_NOLOCK=1)
             atomicAdd(progress, 1ULL);
             if (in_step) {
               const unsigned long long want = point * ncta;

@@ -748,6 +748,31 @@ __global__ void k_wide_v(const double* __restrict__ gr, const double* __restrict
   if (j < m) v[j] = gr[j] / hr[j];
 }
 
+// Replicated batch of the wide branch when its rows are spread over several ranks or held in sparse form: every rank
+// writes its rows at their global position into a zero-initialised column-major buffer W[ldw x (m + 4)] — the m columns of
+// A followed by the row vectors s, res, q, u — and a sum all-reduce makes the batch identical everywhere.
+__global__ void k_wide_gather(const double* __restrict__ A, int64_t ldd, int64_t row0, int nrows, int m,
+                              const double* __restrict__ s, const double* __restrict__ res,
+                              const double* __restrict__ q, const double* __restrict__ u, double* __restrict__ W,
+                              int64_t ldw, int64_t off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= nrows) return;
+  double v;
+  if (j < m)
+    v = A ? A[(int64_t)j * ldd + row0 + i] : 0.0;
+  else
+    v = (j == m ? s : j == m + 1 ? res : j == m + 2 ? q : u)[row0 + i];
+  if (j >= m || A) W[(int64_t)j * ldw + off + i] = v;
+}
+// the A part of the same buffer from the CSR copy of a sparse shard (one thread per row; rows are short)
+__global__ void k_wide_gather_csr(const int64_t* __restrict__ rowptr, const int* __restrict__ colidx,
+                                  const double* __restrict__ vals, int64_t row0, int nrows, double* __restrict__ W,
+                                  int64_t ldw, int64_t off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  for (int64_t p = rowptr[row0 + i]; p < rowptr[row0 + i + 1]; ++p) W[(int64_t)colidx[p] * ldw + off + i] = vals[p];
+}
+
 // ---- pivoted LU fallback (unblocked, right-looking) -------------------------------------------
 // The Cholesky sequence writes the lower triangle only.  When the caller's matrix is symmetric in storage (every Gram
 // this library forms is), the original is therefore still there: upper triangle + a saved diagonal.  No m x m copy.

@@ -246,6 +246,8 @@ struct scs_problem {
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
   double* d_u = nullptr;  // row vector of the GGN wide branch / A d of the line search (ldd doubles, allocated on first use)
+  double *d_wide = nullptr, *d_widepart = nullptr, *d_wcnt = nullptr;  // replicated batch of the GGN wide branch
+  size_t wide_cap = 0, widepart_cap = 0;
   double* d_lspart = nullptr;  // line search: per-block trial sums | 8 sums | f(x), <∇q,d>
   int64_t lspart_cap = 0;
   // sparse shard (kernels_sparse.cuh): CSR + CSC copies, no dense A
@@ -337,6 +339,29 @@ static int run_adjoint(scs_problem* p, const double* dr, double* dout) {
     LAUNCH(c, k_adjoint<8>, (unsigned)blocks, kAdjThreads, 0, p->dA + p->alo, p->ldd, nproc, (int)p->m, dr + p->alo,
            p->d_adjpart);
   LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_adjpart, blocks, (int)p->m, dout);
+  return SCS_OK;
+}
+
+// z_out = A v on the rows of the active window (no loss pieces): the line search's A d
+static int run_matvec(scs_problem* p, const double* dv, double* zout) {
+  scs_ctx* c = p->ctx;
+  StageTimer t(c, ST_FWD);
+  LossParams lp = p->loss;
+  lp.kind = 2;  // z only
+  lp.weight_kind = 0;
+  if (p->sparse) {
+    const int64_t blocks = (p->n + kSpFwdRows - 1) / kSpFwdRows;
+    LAUNCH(c, k_sp_forward, (unsigned)blocks, kSpFwdThreads, 0, (const int64_t*)p->d_rowptr, (const int*)p->d_colidx,
+           (const double*)p->d_vals, p->n, p->win_lo, p->win_hi, dv, (const double*)p->dy, lp, zout, (double*)nullptr,
+           (double*)nullptr, p->d_losspart);
+    return SCS_OK;
+  }
+  const int64_t nproc = p->ahi - p->alo;
+  const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
+  if (blocks > 0)
+    LAUNCH(c, k_forward<8>, (unsigned)blocks, kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc, p->win_lo - p->alo,
+           p->win_hi - p->alo, (int)p->m, dv, p->dy + p->alo, lp, zout + p->alo, (double*)nullptr, (double*)nullptr,
+           p->d_losspart);
   return SCS_OK;
 }
 
@@ -819,10 +844,12 @@ static int i8_launch_syrk(scs_problem* p, const CUtensorMap& amap, const CUtenso
   const int ncl = (int)std::min<int64_t>(p->i8_clusters, pl.units);
   cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
   CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
+  static const bool nolock = getenv("SCS_I8_NOLOCK") && atoi(getenv("SCS_I8_NOLOCK"));
+  unsigned long long* prog = nolock ? nullptr : p->d_i8progress;
   cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, amap, bmap, pl, (const int2*)p->d_i8tiles,
-                                                p->d_i8partial, p->d_i8progress)
+                                                p->d_i8partial, prog)
                            : cudaLaunchKernelEx(&cfg, k_i8syrk, amap, bmap, pl, (const int2*)p->d_i8tiles,
-                                                p->d_i8partial, p->d_i8progress);
+                                                p->d_i8partial, prog);
   c->launches += 1;
   if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
   return SCS_OK;
@@ -1189,15 +1216,17 @@ static int run_solve(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_
 
 // ProxGGNSCORE underdetermined branch (rows + 1 <= m, prox-GGN-SCORE.jl:124-127) on the rows of the active window;
 // leaves gr, Hr, the damping scalars (k_pre) and d (before negation) in d_gr, d_hr, d_scal, d_sol.  See kernels_solve.cuh.
+// The n x n system couples every pair of rows of the batch.  One rank with a dense shard works on its rows in place;
+// several ranks (or a sparse shard) first REPLICATE the batch — it is small by definition, rows < m — into a dense buffer
+// (k_wide_gather + one sum all-reduce) and then every rank runs the same kernels on the same bits: the direction is
+// bitwise identical everywhere, like the rest of the replicated x-side state.
 static int run_ggn_wide(scs_problem* p, XRef x, double lam) {
   scs_ctx* c = p->ctx;
-  if (c->world > 1)
-    return fail(SCS_UNSUPPORTED, "ProxGGNSCORE underdetermined branch (n+1 <= m) needs all rows of the batch on one GPU");
-  if (p->sparse)
-    return fail(SCS_UNSUPPORTED, "ProxGGNSCORE underdetermined branch (n+1 <= m) is not implemented for a sparse shard");
   const int m = (int)p->m;
-  const int nb = (int)(p->win_hi - p->win_lo);
+  const int nbl = (int)(p->win_hi - p->win_lo);  // this rank's rows of the batch (may be 0)
+  const int nb = (int)p->win_rows_global;        // the whole batch
   if (nb < 1) return fail(SCS_INVALID_ARG, "empty batch");
+  const bool repl = c->world > 1 || p->sparse;
   SCS_TRY(gram_setup(p));
   if (!p->d_u) SCS_TRY(dalloc(&p->d_u, p->ldd));
   {
@@ -1205,26 +1234,70 @@ static int run_ggn_wide(scs_problem* p, XRef x, double lam) {
     LAUNCH(c, k_pre, 1, kVecThreads, 0, p->sm, lam, x.d, (const double*)nullptr, m, p->d_gr, p->d_hr, p->d_rhs, p->d_scal);
     LAUNCH(c, k_wide_v, (m + 255) / 256, 256, 0, p->d_gr, p->d_hr, m, p->d_t1);
   }
-  // pieces s, res, q of the (out_fn, f(y,ŷ)) pair for the window's rows -> dz, dr, dw
+  // pieces s, res, q of the (out_fn, f(y,ŷ)) pair for the window's rows -> dz, dr, dw;  u = A (gr ./ Hr) -> d_u
   SCS_TRY(run_forward(p, x.d, 2));
   p->fwd_id = 0;  // not a pass the caches know about (no loss sum, z replaced by s)
   p->grad_id = 0;
   p->loss_reduced = false;
-  {
-    StageTimer t(c, ST_FWD);  // u = A (gr ./ Hr)
-    LossParams lp = p->loss;
-    lp.kind = 2;
-    lp.weight_kind = 0;
-    const int64_t nproc = p->ahi - p->alo;
-    LAUNCH(c, k_forward<8>, (unsigned)((nproc + kFwdRows - 1) / kFwdRows), kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc,
-           p->win_lo - p->alo, p->win_hi - p->alo, m, (const double*)p->d_t1, p->dy + p->alo, lp, p->d_u + p->alo,
-           (double*)nullptr, (double*)nullptr, p->d_losspart);
+  SCS_TRY(run_matvec(p, p->d_t1, p->d_u));
+  const double *Ab = p->dA ? p->dA + p->win_lo : nullptr, *vs = p->dz + p->win_lo, *vres = p->dr + p->win_lo,
+               *vq = p->dw + p->win_lo;
+  double* vu = p->d_u + p->win_lo;
+  int64_t ldb = p->ldd;
+  if (repl) {
+    // where this rank's rows sit inside the batch: exclusive prefix of the per-rank row counts
+    int64_t off = 0;
+    if (c->world > 1) {
+      std::vector<double> cnt(c->world, 0.0);
+      cnt[c->rank] = (double)nbl;
+      if (!p->d_wcnt) SCS_TRY(dalloc(&p->d_wcnt, c->world));
+      CU_TRY(cudaMemcpyAsync(p->d_wcnt, cnt.data(), c->world * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      SCS_TRY(allreduce(c, p->d_wcnt, c->world));
+      CU_TRY(cudaMemcpyAsync(cnt.data(), p->d_wcnt, c->world * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(cudaStreamSynchronize(c->stream));
+      int64_t tot = 0;
+      for (int r = 0; r < c->world; ++r) {
+        if (r < c->rank) off += (int64_t)(cnt[r] + 0.5);
+        tot += (int64_t)(cnt[r] + 0.5);
+      }
+      if (tot != nb) return fail(SCS_STATE_ERROR, "wide GGN branch: the ranks disagree on the batch size");
+    }
+    const int64_t ldw = round_up(nb, 16);
+    const size_t need = (size_t)ldw * (m + 4);
+    if (p->wide_cap < need) {
+      dfree(p->d_wide);
+      p->d_wide = nullptr;
+      SCS_TRY(dalloc(&p->d_wide, need));
+      p->wide_cap = need;
+    }
+    const int64_t blocks = (ldw + 64 * 8 - 1) / (64 * 8);
+    if (p->widepart_cap < (size_t)blocks * m) {
+      dfree(p->d_widepart);
+      p->d_widepart = nullptr;
+      SCS_TRY(dalloc(&p->d_widepart, (size_t)blocks * m));
+      p->widepart_cap = (size_t)blocks * m;
+    }
+    StageTimer t(c, ST_FWD);
+    CU_TRY(cudaMemsetAsync(p->d_wide, 0, need * sizeof(double), c->stream));
+    if (nbl > 0) {
+      LAUNCH(c, k_wide_gather, dim3((nbl + 255) / 256, m + 4), 256, 0, (const double*)p->dA, p->ldd, p->win_lo, nbl, m,
+             (const double*)p->dz, (const double*)p->dr, (const double*)p->dw, (const double*)p->d_u, p->d_wide, ldw, off);
+      if (p->sparse)
+        LAUNCH(c, k_wide_gather_csr, (nbl + 255) / 256, 256, 0, (const int64_t*)p->d_rowptr, (const int*)p->d_colidx,
+               (const double*)p->d_vals, p->win_lo, nbl, p->d_wide, ldw, off);
+    }
+    SCS_TRY(allreduce(c, p->d_wide, need));
+    Ab = p->d_wide;
+    ldb = ldw;
+    vs = p->d_wide + (size_t)m * ldw;
+    vres = vs + ldw;
+    vq = vres + ldw;
+    vu = p->d_wide + (size_t)(m + 3) * ldw;
   }
   StageTimer t(c, ST_SOLVE);
   const int nt = (nb + 63) / 64;
-  LAUNCH(c, k_rowgram, nt * (nt + 1) / 2, 256, 0, p->dA + p->win_lo, p->ldd, nb, m, p->d_hr, p->d_G, nb);
-  LAUNCH(c, k_wide_system, dim3((nb + 255) / 256, nb), 256, 0, p->d_G, nb, nb, p->dz + p->win_lo, p->dr + p->win_lo,
-         p->dw + p->win_lo, p->d_u + p->win_lo, lam, p->d_q);
+  LAUNCH(c, k_rowgram, nt * (nt + 1) / 2, 256, 0, Ab, ldb, nb, m, p->d_hr, p->d_G, nb);
+  LAUNCH(c, k_wide_system, dim3((nb + 255) / 256, nb), 256, 0, p->d_G, nb, nb, vs, vres, vq, (const double*)vu, lam, p->d_q);
   // general (non-symmetric) system: partial-pivoting LU on the device
   CU_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), c->stream));
   for (int k = 0; k < nb; ++k) {
@@ -1233,8 +1306,14 @@ static int run_ggn_wide(scs_problem* p, XRef x, double lam) {
     if (rem > 0) LAUNCH(c, k_lu_update, dim3((rem + 255) / 256, (rem + 15) / 16), 256, 0, p->d_G, (int64_t)nb, nb, k, p->d_q);
   }
   LAUNCH(c, k_lu_backsolve, 1, kVecThreads, 0, p->d_G, (int64_t)nb, nb, p->d_q, p->d_t2);
-  LAUNCH(c, k_wide_scale, (nb + 255) / 256, 256, 0, p->dz + p->win_lo, p->d_t2, nb, p->d_u + p->win_lo);
-  SCS_TRY(run_adjoint(p, p->d_u, p->d_t1));
+  LAUNCH(c, k_wide_scale, (nb + 255) / 256, 256, 0, vs, p->d_t2, nb, vu);
+  if (repl) {  // A'(s ∘ B') from the replicated batch: the same bits on every rank
+    const int64_t blocks = (ldb + 64 * 8 - 1) / (64 * 8);
+    LAUNCH(c, k_adjoint<8>, (unsigned)blocks, kAdjThreads, 0, Ab, ldb, ldb, m, (const double*)vu, p->d_widepart);
+    LAUNCH(c, k_colsum, (unsigned)((m + 31) / 32), 256, 0, p->d_widepart, blocks, m, p->d_t1);
+  } else {
+    SCS_TRY(run_adjoint(p, p->d_u, p->d_t1));
+  }
   LAUNCH(c, k_wide_dir, (m + 255) / 256, 256, 0, p->d_t1, p->d_gr, p->d_hr, lam, m, p->d_sol);
   p->last_used_fallback = 1;
   return SCS_OK;
@@ -1475,7 +1554,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_Gpack, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_Gpack, p->d_wide, p->d_widepart, p->d_wcnt, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
@@ -2018,29 +2097,6 @@ static int compute_gq(scs_problem* p, XRef v, double lam, double* dout) {
   SCS_TRY(ensure_grad(p, v, SCS_WEIGHTS_NEWTON));
   StageTimer t(p->ctx, ST_VEC);
   LAUNCH(p->ctx, k_pre, 1, kVecThreads, 0, p->sm, lam, v.d, p->d_gl, (int)p->m, p->d_t1, p->d_t2, dout, p->d_scal + SC_SCRATCH);
-  return SCS_OK;
-}
-
-// z_out = A v on the rows of the active window (no loss pieces): the line search's A d
-static int run_matvec(scs_problem* p, const double* dv, double* zout) {
-  scs_ctx* c = p->ctx;
-  StageTimer t(c, ST_FWD);
-  LossParams lp = p->loss;
-  lp.kind = 2;  // z only
-  lp.weight_kind = 0;
-  if (p->sparse) {
-    const int64_t blocks = (p->n + kSpFwdRows - 1) / kSpFwdRows;
-    LAUNCH(c, k_sp_forward, (unsigned)blocks, kSpFwdThreads, 0, (const int64_t*)p->d_rowptr, (const int*)p->d_colidx,
-           (const double*)p->d_vals, p->n, p->win_lo, p->win_hi, dv, (const double*)p->dy, lp, zout, (double*)nullptr,
-           (double*)nullptr, p->d_losspart);
-    return SCS_OK;
-  }
-  const int64_t nproc = p->ahi - p->alo;
-  const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
-  if (blocks > 0)
-    LAUNCH(c, k_forward<8>, (unsigned)blocks, kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc, p->win_lo - p->alo,
-           p->win_hi - p->alo, (int)p->m, dv, p->dy + p->alo, lp, zout + p->alo, (double*)nullptr, (double*)nullptr,
-           p->d_losspart);
   return SCS_OK;
 }
 

@@ -94,7 +94,8 @@ def _minibatch_checks(ctx, rank, world):
     n = A.shape[0]
     perm = np.random.default_rng(9).permutation(n)
     At, yt = A[:600] * 1.25, y[:600]
-    for mname, bs in (("ProxLQNSCORE", 700), ("ProxGGNSCORE", 1100)):
+    # bs = 100 < m = 128: every step of that run is the GGN underdetermined branch with the batch rows spread over the ranks
+    for mname, bs in (("ProxLQNSCORE", 700), ("ProxGGNSCORE", 1100), ("ProxGGNSCORE", 100)):
         loss_o = O.LogisticLoss(1 / n, "consistent")
         loss_g = S.LogisticLoss(1 / n, "consistent")
         so = O.iterate(getattr(O, mname)(), O.Problem(A, y, x0, loss_o, 1e-2, Atest=At, ytest=yt), "l1",
@@ -110,7 +111,8 @@ def _minibatch_checks(ctx, rank, world):
             eo = max(abs(a - b) / abs(b) for a, b in zip(sg.obj, so.obj))
             et = max(abs(a - b) / abs(b) for a, b in zip(sg.fvaltest, so.fvaltest))
             assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj) == len(sg.fvaltest), (mname, dl)
-            assert ex <= 1e-10 and eo <= 1e-10 and et <= 1e-10, (mname, dl, rank, ex, eo, et)
+            tol = 1e-9 if bs < A.shape[1] else 1e-10  # the wide branch has a general LU in every step
+            assert ex <= tol and eo <= tol and et <= tol, (mname, bs, dl, rank, ex, eo, et)
             worst = max(worst, ex, eo, et)
             model.close()
     return worst

@@ -288,6 +288,30 @@ def test_sparse_compute_path(scs, method, reg, loss, batch_size):
         pg.close()
 
 
+@pytest.mark.parametrize("n,m,loss,batch_size", [(60, 200, "consistent", None), (150, 400, "ls", None),
+                                                 (3000, 300, "literal", 128)])
+def test_sparse_shard_takes_the_ggn_wide_branch(scs, n, m, loss, batch_size):
+    """ProxGGNSCORE underdetermined branch (rows + 1 <= m, prox-GGN-SCORE.jl:124-127) on a shard that is resident in
+    sparse form: the batch is expanded from the CSR copy into the replicated dense buffer (k_wide_gather_csr), the rest is
+    the dense algorithm.  Whole problem wide, and mini-batches smaller than m of a tall problem."""
+    As, Ad, y, x0 = _sparse_problem(n, m, 0.05, seed=33, loss="ls" if loss == "ls" else "logistic")
+    if loss == "ls":
+        Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
+    else:
+        Lo, Lg = O.LogisticLoss(1 / n, loss), scs.LogisticLoss(1 / n, loss)
+    kw = dict(max_epoch=4, alpha=0.9, batch_size=batch_size)
+    so = O.iterate(O.ProxGGNSCORE(), O.Problem(Ad, y, x0, Lo, 1e-2), "l1", O.PHuberSmootherL1L2(1.0), **kw)
+    for device_loop in (False, True):
+        pg = scs.Problem(As, y, x0, Lg, 1e-2, storage="sparse")
+        assert pg.is_sparse()[0]
+        sg = scs.iterate(scs.ProxGGNSCORE(), pg, "l1", scs.PHuberSmootherL1L2(1.0), verbose=0, device_loop=device_loop,
+                         shuffle_batch=False, **kw)
+        assert sg.epochs == so.epochs and len(sg.obj) == len(so.obj)
+        assert relerr(sg.x, so.x) <= 1e-9, relerr(sg.x, so.x)
+        assert hist_err(sg.obj, so.obj) <= 1e-9
+        pg.close()
+
+
 def test_sparse_components_and_auto_storage(scs):
     import scipy.sparse as sp
     n, m = 3001, 257
