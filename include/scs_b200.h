@@ -207,6 +207,10 @@ int scs_get_stage_ms(scs_ctx* ctx, double* ms, int64_t* calls, int reset);
  * resident in shared memory (no memory traffic) — the denominator bench.py uses for k_i8syrk's roofline.  burst = best of
  * five ~20 ms launches, sustained = back-to-back launches for `seconds`.  TOP/s. */
 int scs_measure_i8_peak(scs_ctx* ctx, double seconds, double* tops_burst, double* tops_sustained);
+/* Tuning aid: TOP/s of k_i8syrk's main loop (4-stage TMA -> UMMA ring, one CTA per SM, no cluster / epilogue / lock-step)
+ * on an operand that stays in L2.  tma_mode 0: operands resident in shared memory, 1: the A slab (16 KB per stage) through
+ * TMA, 2: A and B slabs (48 KB per stage).  Separates the SM-level pipeline limit from DRAM / multicast effects. */
+int scs_i8_pipe_probe(scs_ctx* ctx, int tma_mode, double* tops);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ struct I8Plan {
   int pchunks, pchunk0;
   int main_chunks;        // k_crt: slots [0, main_chunks) carry weight sign_main, the rest sign_extra
   int sign_main, sign_extra;
+  int lock_slack;         // lock-step: a producer may start segment t once all have finished issuing segment t - 1 - lock_slack
 };
 
 // ---- column / row statistics -------------------------------------------------------------------------------
@@ -470,7 +471,7 @@ k_i8syrk(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUten
           if (point > 0 && progress != nullptr) {  // progress == nullptr: free-running (tuning aid SCS_I8_NOLOCK=1)
             atomicAdd(progress, 1ULL);
             if (in_step) {
-              const unsigned long long want = point * ncta;
+              const unsigned long long want = point > (unsigned long long)pl.lock_slack ? (point - pl.lock_slack) * ncta : 0ULL;
               int spins = 0;
               while (true) {
                 unsigned long long seen;
@@ -730,7 +731,7 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
           if (point > 0 && progress != nullptr) {  // progress == nullptr: free-running (tuning aid SCS_I8_NOLOCK=1)
             atomicAdd(progress, 1ULL);
             if (in_step) {
-              const unsigned long long want = point * ncta;
+              const unsigned long long want = point > (unsigned long long)pl.lock_slack ? (point - pl.lock_slack) * ncta : 0ULL;
               int spins = 0;
               while (true) {
                 unsigned long long seen;
@@ -937,6 +938,110 @@ __global__ void __launch_bounds__(128, 1) k_i8peak(long long groups /* of 64 x 4
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kI8TmemCols) : "memory");
+}
+
+// pseudo-random bytes (the toggle rate of the operand bits decides the tensor-pipe power, hence the clock under the cap)
+__global__ void k_fill_random_bytes(uint32_t* __restrict__ p, size_t nwords) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t v = (uint32_t)i * 2654435761u + 0x9e3779b9u;
+    v ^= v >> 15;
+    v *= 0x85ebca6bu;
+    v ^= v >> 13;
+    p[i] = v;
+  }
+}
+
+// ---- pipeline probe (tuning aid): k_i8syrk's main loop on an L2-resident operand ------------------------------------
+// The same 4-stage TMA -> mbarrier -> UMMA ring as k_i8syrk (one CTA per SM, no cluster, no multicast, no epilogue, no
+// lock-step), reading a 24 MB matrix that stays in L2.  tma_mode: 0 = no TMA at all (operands filled once; only the
+// per-stage commit / slot hand-shake remains), 1 = the A slab (16 KB per stage) comes through TMA, 2 = A and B (48 KB per
+// stage, what an unclustered CTA would move).  Separates what the SM-level pipeline can sustain from DRAM / L2-miss /
+// multicast / lock-step effects.
+__global__ void __launch_bounds__(128, 1)
+k_i8pipe(const __grid_constant__ CUtensorMap map /* dims {K bytes, 384 rows, 1}, box {128, 128, 1} */, int tma_mode,
+         long long iters, int kspan /* k-blocks in the matrix */, uint32_t* __restrict__ sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = (uint64_t*)(smem + kI8Stages * kI8StageBytes);
+  uint64_t* empty = full + kI8Stages;
+  uint32_t* tmem_slot = (uint32_t*)(empty + kI8Stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kI8Stages * kI8StageBytes / 4; i += 128)
+    reinterpret_cast<uint32_t*>(smem)[i] = ((uint32_t)i * 2654435761u + blockIdx.x * 40503u) ^ ((uint32_t)i << 13);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kI8Stages; ++q) {
+      mbar_init(&full[q], 1);
+      mbar_init(&empty[q], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kI8TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && lane == 0 && tma_mode > 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int kb = (int)((blockIdx.x * 37u) % (unsigned)kspan);
+    for (long long it = 0; it < iters; ++it) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * kI8StageBytes;
+      mbar_expect_tx(&full[stage], tma_mode == 2 ? kI8StageBytes : kI8ABytes);
+      tma_load_3d(sa, &map, &full[stage], kb * kI8BK, 0, 0);
+      if (tma_mode == 2) {
+        tma_load_3d(sa + kI8ABytes, &map, &full[stage], kb * kI8BK, 128, 0);
+        tma_load_3d(sa + kI8ABytes + kI8ABytes, &map, &full[stage], kb * kI8BK, 256, 0);
+      }
+      if (++kb == kspan) kb = 0;
+      if (++stage == kI8Stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long it = 0; it < iters; ++it) {
+      if (tma_mode > 0) {
+        mbar_wait(&full[stage], phase);
+      } else if (it >= kI8Stages) {
+        mbar_wait(&empty[stage], phase ^ 1);  // the slot's previous group has retired: at most 4 groups are queued
+      }
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kI8StageBytes);
+      const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kI8ABytes);
+      const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * kI8BN);
+#pragma unroll
+      for (int k = 0; k < kI8BK / 32; ++k) umma_i8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kI8Idesc, 1u);
+      tc_commit(&empty[stage]);
+      if (++stage == kI8Stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // drain: the last group's commit
+    const int last = (int)((iters - 1) % kI8Stages);
+    const uint32_t lph = (uint32_t)(((iters - 1) / kI8Stages) & 1);
+    if (iters > 0) mbar_wait(&empty[last], lph);
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base, v);
+    if (sink && v[lane] == 0x7fffffffu) sink[0] = v[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kI8TmemCols) : "memory");
 }
 

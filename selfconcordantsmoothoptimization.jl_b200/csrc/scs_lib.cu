@@ -845,10 +845,13 @@ static int i8_launch_syrk(scs_problem* p, const CUtensorMap& amap, const CUtenso
   cfg.gridDim = dim3((unsigned)(ncl * kI8Cluster));
   CU_TRY(cudaMemsetAsync(p->d_i8progress, 0, sizeof(unsigned long long), c->stream));
   static const bool nolock = getenv("SCS_I8_NOLOCK") && atoi(getenv("SCS_I8_NOLOCK"));
+  static const int slack = getenv("SCS_I8_SLACK") ? atoi(getenv("SCS_I8_SLACK")) : 0;
+  I8Plan plv = pl;
+  plv.lock_slack = slack;
   unsigned long long* prog = nolock ? nullptr : p->d_i8progress;
-  cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, amap, bmap, pl, (const int2*)p->d_i8tiles,
+  cudaError_t le = two_cta ? cudaLaunchKernelEx(&cfg, k_i8syrk2, amap, bmap, plv, (const int2*)p->d_i8tiles,
                                                 p->d_i8partial, prog)
-                           : cudaLaunchKernelEx(&cfg, k_i8syrk, amap, bmap, pl, (const int2*)p->d_i8tiles,
+                           : cudaLaunchKernelEx(&cfg, k_i8syrk, amap, bmap, plv, (const int2*)p->d_i8tiles,
                                                 p->d_i8partial, prog);
   c->launches += 1;
   if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_i8syrk launch: ") + cudaGetErrorString(le));
@@ -1488,6 +1491,60 @@ extern "C" int scs_measure_i8_peak(scs_ctx* c, double seconds, double* tops_burs
   cudaEventDestroy(e1);
   cudaFree(sink);
   CU_TRY(cudaGetLastError());
+  return SCS_OK;
+}
+
+// Tuning aid: TOP/s of k_i8syrk's main loop (4-stage TMA -> UMMA ring, one CTA per SM) on an L2-resident operand.
+// tma_mode 0: operands stay in shared memory (only the per-stage commit / slot hand-shake), 1: the A slab (16 KB per
+// stage) through TMA, 2: A and B (48 KB per stage).  Best of 5 launches of ~15 ms.
+extern "C" int scs_i8_pipe_probe(scs_ctx* c, int tma_mode, double* tops) {
+  if (!c || !tops) return fail(SCS_INVALID_ARG, "NULL argument");
+  if (tma_mode < 0 || tma_mode > 2) return fail(SCS_INVALID_ARG, "tma_mode must be 0, 1 or 2");
+  if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  CU_TRY(cudaSetDevice(c->device));
+  const int kspan = 512;  // 512 k-blocks x 128 bytes x 384 rows = 24 MB: stays in L2
+  const size_t ldk = (size_t)kspan * kI8BK, bytes = ldk * 384;
+  uint8_t* buf = nullptr;
+  uint32_t* sink = nullptr;
+  CU_TRY(cudaMalloc((void**)&buf, bytes));
+  CU_TRY(cudaMalloc((void**)&sink, sizeof(uint32_t)));
+  k_fill_random_bytes<<<1024, 256, 0, c->stream>>>(reinterpret_cast<uint32_t*>(buf), bytes / 4);  // realistic operand bits
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {(cuuint64_t)ldk, 384u, 1u};
+  cuuint64_t gstride[2] = {(cuuint64_t)ldk, (cuuint64_t)ldk * 384u};
+  cuuint32_t box[3] = {(cuuint32_t)kI8BK, 128u, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, buf, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cudaFree(buf);
+    cudaFree(sink);
+    return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (pipe probe) failed");
+  }
+  const int smem = kI8Stages * kI8StageBytes + 1024 + 256;
+  CU_TRY(cudaFuncSetAttribute(k_i8pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  const long long iters = 40000;  // x 4 UMMAs
+  const double ops = (double)iters * (kI8BK / 32) * 2.0 * kI8BM * kI8BN * 32.0 * c->num_sms;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    k_i8pipe<<<c->num_sms, 128, smem, c->stream>>>(map, tma_mode, iters, kspan, sink);
+    c->launches += 1;
+    cudaEventRecord(e1, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+  }
+  *tops = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
   return SCS_OK;
 }
 

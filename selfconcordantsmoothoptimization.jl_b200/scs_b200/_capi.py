@@ -29,7 +29,7 @@ EXPORTS = (
     "scs_ctx_stream", "scs_problem_create", "scs_problem_create_csc", "scs_problem_is_sparse", "scs_problem_create_synthetic", "scs_problem_destroy",
     "scs_problem_read_rows", "scs_set_regularizer", "scs_set_smoother", "scs_set_method", "scs_set_L",
     "scs_set_gram_mode", "scs_get_gram_path", "scs_set_gram_bits", "scs_get_gram_info", "scs_get_gram_signed", "scs_set_stream_mode", "scs_get_stream_path", "scs_set_active_rows", "scs_set_batches", "scs_set_test_problem", "scs_get_test_history", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
-    "scs_smoother_eval", "scs_prox", "scs_reg_value", "scs_get_counters", "scs_set_profiling", "scs_get_stage_ms", "scs_measure_i8_peak",
+    "scs_smoother_eval", "scs_prox", "scs_reg_value", "scs_get_counters", "scs_set_profiling", "scs_get_stage_ms", "scs_measure_i8_peak", "scs_i8_pipe_probe",
 )
 
 
@@ -104,6 +104,7 @@ def lib():
         "scs_set_profiling": ([vp, i32], i32),
         "scs_get_stage_ms": ([vp, _dp, _ip, i32], i32),
         "scs_measure_i8_peak": ([vp, dbl, _dp, _dp], i32),
+        "scs_i8_pipe_probe": ([vp, i32, _dp], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -71,6 +71,12 @@ class Context:
         K.check(K.lib().scs_measure_i8_peak(self._h, float(seconds), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def i8_pipe_probe(self, tma_mode):
+        """TOP/s of k_i8syrk's main loop on an L2-resident operand (tuning aid; tma_mode 0 / 1 / 2, see scs_b200.h)."""
+        a = C.c_double()
+        K.check(K.lib().scs_i8_pipe_probe(self._h, int(tma_mode), C.byref(a)))
+        return a.value
+
     def linear_solve(self, M, b):
         """(H + λHr) \\ ∇q on the device: Cholesky, pivoted-LU fallback.  Returns (d, used_fallback)."""
         M = np.asfortranarray(np.asarray(M, dtype=np.float64))
