@@ -6,7 +6,7 @@ n = 1,000,000 x m = 4096, fp64, ProxGGNSCORE (ss_type 1, alpha = 1), l1 (lambda 
 consistent labels.  A "step" is one solver iteration = objective f(x)+g(x) (iterate.jl:189-190) + step!
 (iterate.jl:233).  With --gpus N the rows are sharded over N ranks (strong scaling: the problem is fixed).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|sparse|sparse_dense]
 
   value   K iterations inside the library (scs_solve: x never leaves HBM), timed with CUDA events on the
           library's stream, barrier + synchronize on both sides, max over ranks.
@@ -58,6 +58,12 @@ WORKLOADS = {
                desc="C4 sparse-group-lasso least squares n=2000000 x m=8192, groups of 64, ProxGGNSCORE"),
     "c5": dict(n=4_000_000, m=4096, loss="ls", method="n", reg="indbox",
                desc="C5 box-constrained least squares n=4000000 x m=4096, ProxNSCORE"),
+    # README.md:105 builds A with sprandn(n, m, 0.01): the same 1 %-dense matrix kept in sparse form on the device
+    # (CSR + CSC copies, csrc/kernels_sparse.cuh); --workload sparse_dense runs the same matrix through the dense kernels
+    "sparse": dict(n=1_000_000, m=4096, loss="logistic", method="ggn", reg="l1", density=0.01, storage="sparse",
+                   desc="README-like sparse logistic regression n=1000000 x m=4096, 1 % dense, sparse storage, ProxGGNSCORE, l1"),
+    "sparse_dense": dict(n=1_000_000, m=4096, loss="logistic", method="ggn", reg="l1", density=0.01, storage="dense",
+                         desc="the same 1 %-dense matrix expanded to the dense layout, ProxGGNSCORE, l1"),
 }
 METRIC = "iters/sec, ProxGGNSCORE 1M×4096 fp64 logreg at 1/2/4/8 B200; % HBM/FP64 roofline"
 
@@ -79,7 +85,8 @@ def build_problem(S, wl, n_total, row0, n_local, ctx, x0):
     else:
         lam = 1e-4
         kw["C_set"] = (-0.5, 0.5)
-    model = S.Problem.synthetic(n_total, m, loss, lam, x0=x0, row0=row0, n_local=n_local, seed=1234, ctx=ctx, **kw)
+    model = S.Problem.synthetic(n_total, m, loss, lam, x0=x0, row0=row0, n_local=n_local, seed=1234, ctx=ctx,
+                                density=wl.get("density", 1.0), storage=wl.get("storage", "dense"), **kw)
     if wl["method"] == "ggn":
         method = S.ProxGGNSCORE()
     elif wl["method"] == "lqn":
@@ -484,7 +491,7 @@ def main():
     gram_path = model.gram_path()  # of the timed steps (the parity check below switches kernels)
     gram_info = model.gram_info()
     parity = None
-    if wl["method"] != "lqn" and not args.no_parity and args.gram != "dmma":
+    if wl["method"] != "lqn" and not args.no_parity and args.gram != "dmma" and gram_path == "i8":
         parity = parity_at_scale(S, method, model, reg, hmu, alpha, x0, rank)
     if world > 1:
         tt = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
@@ -543,6 +550,14 @@ def main():
                           "peak_source": "fp64 cuBLAS DGEMM 8192^3 via torch.matmul, sustained (~1.5 s back to back), measured "
                                          f"live in this run (burst {peak_burst:.1f} TFLOP/s); a frac above 1 is the point of the "
                                          "emulation: fp64 results at int8 tensor-core speed"}
+        elif g_calls and gram_path == "sparse":
+            macs = float(nnz) * (float(nnz) / nl)  # sum over rows of nnz_i^2 ~ nnz * mean row length (uniform sparsity)
+            roof = {"bound": "latency", "kernel": "k_sp_gram (one warp per column, shared-memory accumulator, no atomics)",
+                    "achieved": 2.0 * macs / (g_ms / g_calls * 1e-3) / 1e9, "peak": None, "unit": "GFLOP/s", "frac": None,
+                    "traffic": None, "algorithmic_flops_per_launch": 2.0 * macs, "ms_per_launch": g_ms / g_calls,
+                    "launches_timed": g_calls, "nnz": nnz,
+                    "note": "gather / scatter bound (random shared-memory updates), not a streaming or tensor kernel; the "
+                            "dense int8 path on the expanded matrix is the alternative (--workload sparse_dense)"}
         elif g_calls:
             flops = float(nl) * m * (m + 1)
             ach = flops / (g_ms / g_calls * 1e-3) / 1e12
@@ -553,10 +568,15 @@ def main():
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": g_ms / g_calls, "launches_timed": g_calls}
         stream = {}
         kname = {"forward": "k_forward", "adjoint": "k_adjoint", "fused": "k_fused_grad"}
+        is_sparse, nnz = model.is_sparse()
+        if is_sparse:
+            kname = {"forward": "k_sp_forward", "adjoint": "k_sp_adjoint", "fused": "-"}
         for nm in ("fused", "forward", "adjoint"):
             s_ms, s_calls = stages[nm]
             if s_calls:
-                by = 8.0 * nl * m  # one read of A: forward z=Ax, adjoint g=A'r, or the fused pass doing both
+                # one read of A: forward z=Ax, adjoint g=A'r, or the fused pass doing both; a sparse shard moves 12 bytes
+                # per stored entry and pass (fp64 value + 32-bit index)
+                by = 12.0 * nnz if is_sparse else 8.0 * nl * m
                 ach = by / (s_ms / s_calls * 1e-3) / 1e9
                 stream[nm] = {"bound": "hbm", "kernel": kname[nm], "achieved": ach, "peak": hbm, "unit": "GB/s",
                               "frac": ach / hbm, "algorithmic_bytes_per_launch": by, "ms_per_launch": s_ms / s_calls,
@@ -565,7 +585,7 @@ def main():
             k = next(iter(stream))
             roof = dict(stream[k])
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not is_sparse and "density" not in wl:
             n_s = min(cpu_sample_rows(wl), n_local)
             As, ys = model.read_rows(0, n_s)
             ctl, threads = blas_threads(host_cores())

@@ -101,6 +101,10 @@ int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const int64_t* r
                            int64_t index_base, int64_t n_local, int64_t m, const double* y, int loss_kind,
                            double loss_param, int label_mode, int storage, scs_problem** out);
 int scs_problem_is_sparse(scs_problem* p, int* sparse, int64_t* nnz);
+/* Drops the explicit zeros of a dense resident shard and keeps it in the sparse layout instead (CSR + CSC copies built on
+ * the device, the dense matrix is freed).  For benchmark-sized synthetic shards (scs_problem_create_synthetic with
+ * density < 1, the README's sprandn(n, m, 0.01) look-alike): call right after creation, before the first pass. */
+int scs_problem_sparsify(scs_problem* p);
 /* Synthetic shard generated on the device (bench / full-size invariants): rows [row0,row0+n_local) of the
  * n_total x m problem of oracle/synth.py (Philox-4x32-10, seed).  task: 0 = logistic labels, 1 = LS targets. */
 int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64_t row0, int64_t n_local, int64_t m,

@@ -100,4 +100,115 @@ k_sp_gram(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, co
   }
 }
 
+// ---- dense -> sparse conversion on the device (benchmark-sized synthetic shards: the generator fills the dense layout,
+// explicit zeros are then dropped; nothing crosses PCIe) ---------------------------------------------------------------
+// counts[i] = stored entries of row i (thread per row; adjacent threads read adjacent rows of a column: coalesced)
+__global__ void __launch_bounds__(256) k_nnz_rows(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
+                                                  int64_t* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  int64_t c = 0;
+  for (int j = 0; j < m; ++j) c += A[(int64_t)j * ldd + i] != 0.0 ? 1 : 0;
+  counts[i] = c;
+}
+// counts[j] = stored entries of column j (CTA per column)
+__global__ void __launch_bounds__(256) k_nnz_cols(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
+                                                  int64_t* __restrict__ counts) {
+  __shared__ double red[32];
+  const double* col = A + (int64_t)blockIdx.x * ldd;
+  double c = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) c += col[i] != 0.0 ? 1.0 : 0.0;
+  c = block_sum<256>(c, red);
+  if (threadIdx.x == 0) counts[blockIdx.x] = (int64_t)c;
+}
+// In-place exclusive scan of `data[0..n)` (data[n] receives the total) in three launches: per-block scans of 2048 entries,
+// a single-CTA scan of the block totals, and the add-back.
+constexpr int kScanBlock = 2048;
+__global__ void __launch_bounds__(256) k_scan_blocks(int64_t* __restrict__ data, int64_t n, int64_t* __restrict__ btot) {
+  __shared__ int64_t wsum[8];
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * 8;
+  int64_t v[8], t = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q] = base + q < n ? data[base + q] : 0;
+    t += v[q];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t inc = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  int64_t off = inc - t;
+  for (int q = 0; q < wid; ++q) off += wsum[q];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (base + q < n) data[base + q] = off;
+    off += v[q];
+  }
+  if (threadIdx.x == 255) btot[blockIdx.x] = off;
+}
+__global__ void __launch_bounds__(1) k_scan_top(int64_t* __restrict__ btot, int64_t nb, int64_t* __restrict__ total) {
+  int64_t run = 0;
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t v = btot[b];
+    btot[b] = run;
+    run += v;
+  }
+  total[0] = run;
+}
+__global__ void __launch_bounds__(256) k_scan_add(int64_t* __restrict__ data, int64_t n, const int64_t* __restrict__ btot) {
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * 8;
+  const int64_t off = btot[blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (base + q < n) data[base + q] += off;
+}
+// CSR fill: thread per row, columns ascending
+__global__ void __launch_bounds__(256) k_fill_csr(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
+                                                  const int64_t* __restrict__ rowptr, int* __restrict__ colidx,
+                                                  double* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  int64_t p = rowptr[i];
+  for (int j = 0; j < m; ++j) {
+    const double v = A[(int64_t)j * ldd + i];
+    if (v != 0.0) {
+      colidx[p] = j;
+      vals[p] = v;
+      ++p;
+    }
+  }
+}
+// CSC fill: CTA per column, rows ascending (ballot compaction, 256 rows per round)
+__global__ void __launch_bounds__(256) k_fill_csc(const double* __restrict__ A, int64_t ldd, int64_t n, int m,
+                                                  const int64_t* __restrict__ colptr, int* __restrict__ rowidx,
+                                                  double* __restrict__ cvals) {
+  __shared__ int wcnt[8];
+  const double* col = A + (int64_t)blockIdx.x * ldd;
+  int64_t p = colptr[blockIdx.x];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t i0 = 0; i0 < n; i0 += 256) {
+    const int64_t i = i0 + threadIdx.x;
+    const double v = i < n ? col[i] : 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
+    if (lane == 0) wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << lane) - 1u)), tot = 0;
+    for (int q = 0; q < 8; ++q) {
+      if (q < wid) before += wcnt[q];
+      tot += wcnt[q];
+    }
+    if (v != 0.0) {
+      rowidx[p + before] = (int)i;
+      cvals[p + before] = v;
+    }
+    p += tot;
+    __syncthreads();
+  }
+}
+
 }  // namespace scs

@@ -1793,6 +1793,65 @@ extern "C" int scs_problem_create_synthetic(scs_ctx* ctx, int64_t n_total, int64
   return SCS_OK;
 }
 
+// exclusive scan of counts[0..n) in place, counts[n] = total (device)
+static int device_scan(scs_ctx* c, int64_t* counts, int64_t n) {
+  const int64_t nb = (n + kScanBlock - 1) / kScanBlock;
+  int64_t* btot = nullptr;
+  CU_TRY(cudaMalloc((void**)&btot, std::max<int64_t>(nb, 1) * sizeof(int64_t)));
+  LAUNCH(c, k_scan_blocks, (unsigned)nb, 256, 0, counts, n, btot);
+  LAUNCH(c, k_scan_top, 1, 1, 0, btot, nb, counts + n);
+  LAUNCH(c, k_scan_add, (unsigned)nb, 256, 0, counts, n, (const int64_t*)btot);
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(btot);
+  return SCS_OK;
+}
+
+// Turn a dense resident shard into the sparse layout (CSR + CSC copies) on the device and free the dense matrix.  For
+// benchmark-sized synthetic shards (scs_problem_create_synthetic with density < 1): must be called before the first pass.
+extern "C" int scs_problem_sparsify(scs_problem* p) {
+  if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
+  if (p->sparse) return SCS_OK;
+  if (p->loss.kind == SCS_LOSS_QUADFORM || p->m > 28160 || p->n >= (1LL << 31))
+    return fail(SCS_UNSUPPORTED, "sparse storage needs m <= 28160, n_local < 2^31 and a row-separable loss");
+  if (p->gram_ready || p->i8_ready || p->fu_ready || p->fwd_id != 0)
+    return fail(SCS_STATE_ERROR, "scs_problem_sparsify must be called right after the problem was created");
+  scs_ctx* c = p->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  const int64_t n = p->n;
+  const int m = (int)p->m;
+  CU_TRY(cudaMalloc((void**)&p->d_rowptr, (n + 1) * sizeof(int64_t)));
+  CU_TRY(cudaMalloc((void**)&p->d_colptr, (m + 1) * sizeof(int64_t)));
+  LAUNCH(c, k_nnz_rows, (unsigned)((n + 255) / 256), 256, 0, (const double*)p->dA, p->ldd, n, m, p->d_rowptr);
+  LAUNCH(c, k_nnz_cols, (unsigned)m, 256, 0, (const double*)p->dA, p->ldd, n, m, p->d_colptr);
+  SCS_TRY(device_scan(c, p->d_rowptr, n));
+  SCS_TRY(device_scan(c, p->d_colptr, m));
+  int64_t nnz = 0, nnz2 = 0;
+  CU_TRY(cudaMemcpy(&nnz, p->d_rowptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&nnz2, p->d_colptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (nnz != nnz2) return fail(SCS_STATE_ERROR, "sparsify: row and column counts disagree");
+  const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+  CU_TRY(cudaMalloc((void**)&p->d_colidx, nz * sizeof(int)));
+  CU_TRY(cudaMalloc((void**)&p->d_rowidx, nz * sizeof(int)));
+  CU_TRY(cudaMalloc((void**)&p->d_vals, nz * sizeof(double)));
+  CU_TRY(cudaMalloc((void**)&p->d_cvals, nz * sizeof(double)));
+  LAUNCH(c, k_fill_csr, (unsigned)((n + 255) / 256), 256, 0, (const double*)p->dA, p->ldd, n, m,
+         (const int64_t*)p->d_rowptr, p->d_colidx, p->d_vals);
+  LAUNCH(c, k_fill_csc, (unsigned)m, 256, 0, (const double*)p->dA, p->ldd, n, m, (const int64_t*)p->d_colptr, p->d_rowidx,
+         p->d_cvals);
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  dfree(p->dA);
+  p->dA = nullptr;
+  dfree(p->d_adjpart);
+  p->d_adjpart = nullptr;
+  p->sparse = true;
+  p->nnz = nnz;
+  p->fwd_blocks = (n + kSpFwdRows - 1) / kSpFwdRows;
+  dfree(p->d_losspart);
+  p->d_losspart = nullptr;
+  SCS_TRY(dalloc(&p->d_losspart, p->fwd_blocks));
+  return SCS_OK;
+}
+
 extern "C" int scs_problem_read_rows(scs_problem* p, int64_t row0, int64_t nrows, double* A_out, double* y_out) {
   if (!p) return fail(SCS_INVALID_ARG, "problem is NULL");
   if (row0 < 0 || nrows < 0 || row0 + nrows > p->n) return fail(SCS_INVALID_ARG, "row range outside the shard");

@@ -26,7 +26,7 @@ STAGES = ("forward", "adjoint", "gram", "solve", "vector", "allreduce", "fused",
 # every symbol include/scs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "scs_version", "scs_last_error", "scs_comm_unique_id", "scs_ctx_create", "scs_ctx_destroy", "scs_ctx_sync",
-    "scs_ctx_stream", "scs_problem_create", "scs_problem_create_csc", "scs_problem_is_sparse", "scs_problem_create_synthetic", "scs_problem_destroy",
+    "scs_ctx_stream", "scs_problem_create", "scs_problem_create_csc", "scs_problem_is_sparse", "scs_problem_sparsify", "scs_problem_create_synthetic", "scs_problem_destroy",
     "scs_problem_read_rows", "scs_set_regularizer", "scs_set_smoother", "scs_set_method", "scs_set_L",
     "scs_set_gram_mode", "scs_get_gram_path", "scs_set_gram_bits", "scs_get_gram_info", "scs_get_gram_signed", "scs_set_stream_mode", "scs_get_stream_path", "scs_set_active_rows", "scs_set_batches", "scs_set_test_problem", "scs_get_test_history", "scs_method_init", "scs_objective", "scs_step", "scs_solve", "scs_loss_eval", "scs_gram", "scs_linear_solve",
     "scs_smoother_eval", "scs_prox", "scs_reg_value", "scs_get_counters", "scs_set_profiling", "scs_get_stage_ms", "scs_measure_i8_peak", "scs_i8_pipe_probe",
@@ -72,6 +72,7 @@ def lib():
         "scs_problem_create": ([vp, _dp, i64, i64, i64, _dp, i32, dbl, i32, C.POINTER(vp)], i32),
         "scs_problem_create_csc": ([vp, _ip, _ip, _dp, i64, i64, i64, _dp, i32, dbl, i32, i32, C.POINTER(vp)], i32),
         "scs_problem_is_sparse": ([vp, C.POINTER(i32), _ip], i32),
+        "scs_problem_sparsify": ([vp], i32),
         "scs_problem_create_synthetic": ([vp, i64, i64, i64, i64, i32, dbl, i32, u64, dbl, C.POINTER(vp)], i32),
         "scs_problem_destroy": ([vp], i32),
         "scs_problem_read_rows": ([vp, i64, i64, _dp, _dp], i32),

@@ -286,13 +286,16 @@ class Problem:
         K.check(K.lib().scs_set_batches(self._h, len(off) - 1, K.iptr(off)))
 
     @classmethod
-    def synthetic(cls, n_total, m, f, lam, *, x0=None, row0=0, n_local=None, seed=1234, density=1.0, ctx=None, **kw):
+    def synthetic(cls, n_total, m, f, lam, *, x0=None, row0=0, n_local=None, seed=1234, density=1.0, ctx=None,
+                  storage="dense", **kw):
         """Benchmark-sized shard generated directly in HBM (oracle/synth.py twin)."""
         self = cls(None, None, np.zeros(m) if x0 is None else x0, f, lam, ctx=ctx, **kw)
         n_local = n_total - row0 if n_local is None else n_local
         self.n, self.m = n_local, m
         K.check(K.lib().scs_problem_create_synthetic(self.ctx._h, n_total, row0, n_local, m, f.kind, f.param(),
                                                      f.label_code(), seed, density, C.byref(self._h)))
+        if storage == "sparse":  # drop the zeros on the device: CSR + CSC copies, the dense matrix is freed
+            K.check(K.lib().scs_problem_sparsify(self._h))
         return self
 
     # -- helpers -------------------------------------------------------------------------------

@@ -17,12 +17,45 @@ import scs_b200 as S  # noqa: E402
 from oracle import scs_oracle as O  # noqa: E402
 
 
+def _gram_exchange_checks(ctx, rank, world):
+    """The Gram exchange step itself, on a shape that takes the slab-pipelined packed-triangle all-reduce (m >= 2048: four
+    slabs; emulated-fp64 Gram forced) and on the plain full-square all-reduce of the DMMA path: the all-reduced matrix on
+    every rank against A' diag(w) A of the whole problem in fp64, and bitwise identical across the ranks."""
+    from oracle import synth
+    n, m = 9000, 2100
+    A = synth.make_A(n, m, seed=21)
+    y = synth.make_labels_logistic(A @ synth.make_x_true(m, seed=22, frac=0.2), seed=23)
+    x = synth.make_x0(m, seed=24) * 0.4
+    Lo = O.LogisticLoss(1 / n, "consistent")
+    w = Lo.ggn_weights(A @ x, y)[1]
+    Gref = A.T @ (w[:, None] * A)
+    d = np.sqrt(np.diag(Gref))
+    r0, nl = S.shard_rows(n, world, rank)
+    model = S.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x, S.LogisticLoss(1 / n, "consistent"), 1e-2, ctx=ctx)
+    worst = 0.0
+    for mode in ("i8", "dmma"):
+        model.set_gram_mode(mode)
+        G = model.gram(x, weights="ggn")
+        assert model.gram_path() == mode
+        err = float(np.max(np.abs(G - Gref) / np.outer(d, d)))
+        assert err <= 2e-12, (mode, rank, err)
+        assert np.array_equal(G, G.T)
+        t = torch.from_numpy(np.ascontiguousarray(G)).cuda()
+        lst = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(lst, t)
+        assert all(torch.equal(lst[0], u) for u in lst), mode
+        worst = max(worst, err)
+    model.close()
+    return worst
+
+
 def run_checks(ctx, rank, world, quick=False):
     """Multi-rank parity against the full-batch oracle; torch.distributed must be initialised (NCCL).  Returns the worst
     relative error seen.  quick: two configurations only (bench.py --selftest)."""
     worst = 0.0
     names = ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1") if quick else ("c2_logreg_ggn_l1", "c3_logreg_lqn_l1", "c4_ls_ggn_gl", "c5_ls_n_indbox")
     worst = _full_batch_checks(ctx, rank, world, names)
+    worst = max(worst, _gram_exchange_checks(ctx, rank, world))
     if not quick:
         worst = max(worst, _minibatch_checks(ctx, rank, world))
     return worst
@@ -105,8 +138,9 @@ def _minibatch_checks(ctx, rank, world):
         t0, tl = S.shard_rows(600, world, rank)
         for dl in (False, True):
             model = S.Problem(A[rows], y[rows], x0, loss_g, 1e-2, ctx=ctx, Atest=At[t0:t0 + tl], ytest=yt[t0:t0 + tl])
+            # local_max_iter also makes iterate! run a single epoch (iterate.jl:58-70); the offsets already hold 3 batches
             sg = S.iterate(getattr(S, mname)(), model, "l1", S.PHuberSmootherL1L2(1.0), max_epoch=4, alpha=1,
-                           verbose=0, device_loop=dl, batch_offsets=loc)
+                           verbose=0, device_loop=dl, batch_offsets=loc, local_max_iter=3)
             ex = np.linalg.norm(sg.x - so.x) / np.linalg.norm(so.x)
             eo = max(abs(a - b) / abs(b) for a, b in zip(sg.obj, so.obj))
             et = max(abs(a - b) / abs(b) for a, b in zip(sg.fvaltest, so.fvaltest))

@@ -312,6 +312,35 @@ def test_sparse_shard_takes_the_ggn_wide_branch(scs, n, m, loss, batch_size):
         pg.close()
 
 
+def test_device_side_sparsify_of_a_synthetic_shard(scs):
+    """Problem.synthetic(density=..., storage="sparse"): the generator fills the dense layout in HBM, scs_problem_sparsify
+    drops the zeros on the device (CSR + CSC copies, k_nnz_* / k_scan_* / k_fill_*).  The sparse shard must give the same
+    passes, Gram and iterates as the dense shard generated from the same seed."""
+    n, m = 20_000, 300
+    L = scs.LogisticLoss(1 / n, "consistent")
+    x0 = np.random.default_rng(5).standard_normal(m) * 0.3
+    pd = scs.Problem.synthetic(n, m, L, 1e-3, x0=x0, density=0.02, storage="dense")
+    ps = scs.Problem.synthetic(n, m, L, 1e-3, x0=x0, density=0.02, storage="sparse")
+    sp_flag, nnz = ps.is_sparse()
+    Ad, yd = pd.read_rows(0, n)
+    assert sp_flag and nnz == int(np.count_nonzero(Ad)) and 0.015 * n * m < nnz < 0.025 * n * m
+    fd, gd, zd, rd, wd = pd.loss_eval(x0, weights="ggn", want_rows=True)
+    fs, gs, zs, rs, ws = ps.loss_eval(x0, weights="ggn", want_rows=True)
+    assert abs(fs - fd) <= 1e-13 * abs(fd) and relerr(gs, gd) <= 1e-12
+    np.testing.assert_allclose(zs, zd, rtol=1e-12, atol=1e-15)
+    Gd, Gs = pd.gram(x0, weights="ggn"), ps.gram(x0, weights="ggn")
+    assert ps.gram_path() == "sparse"
+    d = np.sqrt(np.diag(Gd))
+    assert np.max(np.abs(Gs - Gd) / np.outer(d, d)) <= 1e-12
+    sd = scs.iterate(scs.ProxGGNSCORE(), pd, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=5, alpha=1, verbose=0, device_loop=True)
+    ss = scs.iterate(scs.ProxGGNSCORE(), ps, "l1", scs.PHuberSmootherL1L2(1.0), max_epoch=5, alpha=1, verbose=0, device_loop=True)
+    assert relerr(ss.x, sd.x) <= TOL and hist_err(ss.obj, sd.obj) <= TOL and np.array_equal(ss.x != 0, sd.x != 0)
+    with pytest.raises(scs.ScsError):
+        scs._capi.check(scs._capi.lib().scs_problem_sparsify(pd._h))  # only right after creation
+    pd.close()
+    ps.close()
+
+
 def test_sparse_components_and_auto_storage(scs):
     import scipy.sparse as sp
     n, m = 3001, 257
