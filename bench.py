@@ -488,6 +488,7 @@ def main():
         last = fv + rv
     barrier()
     t_e2e = time.perf_counter() - t0
+    is_sparse, nnz = model.is_sparse()
     gram_path = model.gram_path()  # of the timed steps (the parity check below switches kernels)
     gram_info = model.gram_info()
     parity = None
@@ -568,7 +569,6 @@ def main():
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": g_ms / g_calls, "launches_timed": g_calls}
         stream = {}
         kname = {"forward": "k_forward", "adjoint": "k_adjoint", "fused": "k_fused_grad"}
-        is_sparse, nnz = model.is_sparse()
         if is_sparse:
             kname = {"forward": "k_sp_forward", "adjoint": "k_sp_adjoint", "fused": "-"}
         for nm in ("fused", "forward", "adjoint"):

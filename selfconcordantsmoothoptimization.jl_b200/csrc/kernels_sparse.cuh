@@ -7,10 +7,10 @@
 //   k_sp_forward : z_i = sum_p val_p x[col_p] per row (8 lanes per row), then the same loss_row as the dense pass.
 //   k_sp_adjoint : g_j = sum_p val_p r[row_p] per column (one warp per column, fixed shuffle tree).
 //   k_sp_gram    : column k of G = A' diag(w) A:  sum over the stored rows i of column k of (w_i a_ik) * (row i of A),
-//                  accumulated in a shared-memory vector of m doubles by ONE warp in a fixed order (row after row, lane
-//                  l takes the l-th, (l+32)-th ... entry of the row: distinct columns, so no two lanes ever touch the same
-//                  address) => deterministic without atomics.  The lower triangle is then mirrored.
-// All reductions use fixed trees: results are bit-reproducible.
+//                  accumulated by the 8 warps of a CTA in a shared-memory vector of m 64-bit FIXED-POINT integers with
+//                  integer atomics (order-independent => deterministic although the warps interleave freely).  The
+//                  lower triangle is then mirrored.
+// All reductions use fixed trees or exact integer addition: results are bit-reproducible.
 #pragma once
 #include "common.cuh"
 #include "kernels_stream.cuh"
@@ -74,29 +74,65 @@ k_sp_adjoint(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx,
   if (lane == 0) g[j] = s;
 }
 
-// Column k of G (all m entries) into G[:, k]; one warp per CTA, dynamic shared memory = m doubles.
-__global__ void __launch_bounds__(32)
+// Sparse Gram, column by column (Gustavson with a dense accumulator), all 8 warps of a CTA on the same column:
+//   G[j, k] = sum over the stored rows i of column k of (w_i a_ik) a_ij,   j >= k  (the lower triangle; mirrored afterwards)
+// Warp q takes rows q, q + 8, ... of the column, its lanes the entries of a row.  The warps meet in ONE shared accumulator,
+// so the additions are made ORDER-INDEPENDENT instead of ordered: every addend is converted to 64-bit fixed point and added
+// with an integer shared-memory atomic — integer addition is associative, the result is bit-reproducible whatever the
+// interleaving.  Scaling: with cs_j = 1 / sqrt(sum_i |w_i| a_ij^2) (k_sp_colscale) every scaled entry satisfies
+// |G_jk cs_j cs_k| <= 1 (Cauchy-Schwarz on the absolute values, which also bounds every partial sum), so addends are taken
+// as rint(x 2^61): at most 0.5 * 2^-61 off each, <= nnz_col * 2^-62 ~ 1e-15 of the diagonal scale in the worst case.
+// A non-finite addend (NaN / Inf weight) poisons the column like it would in floating point.
+__global__ void __launch_bounds__(256)
+k_sp_colscale(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ cvals,
+              const double* __restrict__ w, int m, double* __restrict__ cs) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= m) return;
+  double a = 0.0;
+  for (int64_t p = colptr[j] + lane; p < colptr[j + 1]; p += 32) a = fma(fabs(w[rowidx[p]]), cvals[p] * cvals[p], a);
+  a = warp_sum(a);
+  if (lane == 0) cs[j] = a > 0.0 ? 1.0 / sqrt(a) : 0.0;  // NaN sums compare false: the column scale 0 makes cinv = 0 ...
+}
+constexpr double kSpFix = 2305843009213693952.0;  // 2^61
+__global__ void __launch_bounds__(256)
 k_sp_gram(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ cvals,
           const int64_t* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
-          const double* __restrict__ w, int m, double* __restrict__ G) {
-  extern __shared__ double acc[];
-  const int lane = threadIdx.x;
+          const double* __restrict__ w, const double* __restrict__ cs, int m, double* __restrict__ G) {
+  extern __shared__ long long sp_acc[];
+  __shared__ int s_bad;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   for (int k = blockIdx.x; k < m; k += gridDim.x) {
-    for (int j = lane; j < m; j += 32) acc[j] = 0.0;
-    __syncwarp();
+    for (int j = k + threadIdx.x; j < m; j += 256) sp_acc[j] = 0;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const double sk = cs[k] * kSpFix;
     const int64_t p1 = colptr[k + 1];
-    for (int64_t p = colptr[k]; p < p1; ++p) {
+    for (int64_t p = colptr[k] + wq; p < p1; p += 8) {
       const int i = rowidx[p];
-      const double c = w[i] * cvals[p];
+      const double wi = w[i];
+      const double c = wi * cvals[p] * sk;
+      if (!(fabs(wi) < 1.0e300)) s_bad = 1;  // NaN / Inf weight (benign race: every writer stores 1)
       if (c != 0.0) {  // rows outside the active mini-batch carry w = 0
         const int64_t q1 = rowptr[i + 1];
-        for (int64_t q = rowptr[i] + lane; q < q1; q += 32) acc[colidx[q]] = fma(c, vals[q], acc[colidx[q]]);
+        for (int64_t q = rowptr[i] + lane; q < q1; q += 32) {
+          const int j = colidx[q];
+          if (j >= k) atomicAdd(reinterpret_cast<unsigned long long*>(&sp_acc[j]),
+                                (unsigned long long)__double2ll_rn(c * (vals[q] * cs[j])));
+        }
       }
-      __syncwarp();
     }
+    __syncthreads();
     double* out = G + (int64_t)k * m;
-    for (int j = lane; j < m; j += 32) out[j] = acc[j];
-    __syncwarp();
+    const bool bad = s_bad != 0;
+    const double ck = cs[k];
+    for (int j = k + threadIdx.x; j < m; j += 256) {
+      const double den = cs[j] * ck * kSpFix;
+      double g = den > 0.0 ? (double)sp_acc[j] / den : 0.0;
+      if (bad) g = __longlong_as_double(0x7ff8000000000000LL);
+      out[j] = g;
+    }
+    __syncthreads();
   }
 }
 

@@ -255,7 +255,7 @@ struct scs_problem {
   int64_t nnz = 0;
   int64_t *d_rowptr = nullptr, *d_colptr = nullptr;
   int *d_colidx = nullptr, *d_rowidx = nullptr;
-  double *d_vals = nullptr, *d_cvals = nullptr;
+  double *d_vals = nullptr, *d_cvals = nullptr, *d_spscale = nullptr;
   // held-out data (model.Atest / model.ytest): a second resident shard whose loss is recorded next to every history
   // entry of scs_solve (ftest, iterate.jl:169-176; utils.jl:55-57)
   scs_problem* test = nullptr;
@@ -999,21 +999,24 @@ static int run_gram(scs_problem* p, XRef x) {
     p->last_gram_path = 3;
     {
       StageTimer t(c, ST_GRAM);
-      const size_t smem = (size_t)m * sizeof(double);
+      const size_t smem = (size_t)m * sizeof(long long);
       size_t& attr_smem = c->sp_gram_smem;  // function attributes are per device: cached in the context
       if (smem > attr_smem) {
         if (smem > 220 * 1024) return fail(SCS_UNSUPPORTED, "sparse Gram: m > 28160 is not supported");
         CU_TRY(cudaFuncSetAttribute(k_sp_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
       }
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
+      if (!p->d_spscale) SCS_TRY(dalloc(&p->d_spscale, m));
+      LAUNCH(c, k_sp_colscale, (unsigned)((m + 7) / 8), 256, 0, (const int64_t*)p->d_colptr, (const int*)p->d_rowidx,
+             (const double*)p->d_cvals, (const double*)p->dw, m, p->d_spscale);
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem + 64, 1)));
       const int grid = std::min(m, c->num_sms * per_sm);
-      LAUNCH(c, k_sp_gram, grid, 32, smem, (const int64_t*)p->d_colptr, (const int*)p->d_rowidx, (const double*)p->d_cvals,
-             (const int64_t*)p->d_rowptr, (const int*)p->d_colidx, (const double*)p->d_vals, (const double*)p->dw, m,
-             p->d_G);
+      LAUNCH(c, k_sp_gram, grid, 256, smem, (const int64_t*)p->d_colptr, (const int*)p->d_rowidx, (const double*)p->d_cvals,
+             (const int64_t*)p->d_rowptr, (const int*)p->d_colidx, (const double*)p->d_vals, (const double*)p->dw,
+             (const double*)p->d_spscale, m, p->d_G);
     }
     {
-      StageTimer t(c, ST_GRAMFIN);  // the two triangles were summed in different orders: keep the lower, mirror it
+      StageTimer t(c, ST_GRAMFIN);  // k_sp_gram wrote the lower triangle of every column: mirror it
       LAUNCH(c, k_symmetrize, dim3((m + 255) / 256, m), 256, 0, p->d_G, (int64_t)m, m);
     }
     SCS_TRY(allreduce(c, p->d_G, (size_t)m * m));
@@ -1611,7 +1614,7 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
                   p->d_gnewton, p->d_scal, p->d_losspart, p->d_adjpart, p->d_G, p->d_Gsave, p->d_partial, p->d_Linv,
                   p->d_info,  p->d_S,     p->d_Y,    p->d_state, p->d_rlb,    p->d_rub,   p->d_slb,    p->d_sub,
                   p->d_cdiag, p->d_ind,   p->d_perm,  p->d_planes, p->d_i8partial, p->d_colmax, p->d_wstat,
-                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_Gpack, p->d_wide, p->d_widepart, p->d_wcnt, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
+                  p->d_colscale, p->d_colinv, p->d_colnorm2, p->d_i8tiles, p->d_i8progress, p->d_cplanes, p->d_negbase, p->d_wpart, p->d_lspart, p->d_spscale, p->d_Gpack, p->d_wide, p->d_widepart, p->d_wcnt, p->d_fupart, p->d_fuloss, p->d_u, p->d_rowptr,
                   p->d_colptr, p->d_colidx, p->d_rowidx, p->d_vals, p->d_cvals};
   for (void* b : bufs) dfree(b);
   if (p->h_scal) cudaFreeHost(p->h_scal);
