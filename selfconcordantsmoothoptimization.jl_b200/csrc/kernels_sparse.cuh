@@ -95,31 +95,83 @@ k_sp_colscale(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx
   if (lane == 0) cs[j] = a > 0.0 ? 1.0 / sqrt(a) : 0.0;  // NaN sums compare false: the column scale 0 makes cinv = 0 ...
 }
 constexpr double kSpFix = 2305843009213693952.0;  // 2^61
+#ifndef SCS_SP_ROWS
+#define SCS_SP_ROWS 2
+#endif
+constexpr int kSpRows = SCS_SP_ROWS;  // stored rows a warp keeps in flight
 __global__ void __launch_bounds__(256)
 k_sp_gram(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ cvals,
           const int64_t* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
           const double* __restrict__ w, const double* __restrict__ cs, int m, double* __restrict__ G) {
-  extern __shared__ long long sp_acc[];
+  // 64-bit accumulators kept as two 32-bit halves: shared memory has native 32-bit atomic adds (ATOMS.ADD) but a 64-bit
+  // add compiles to a compare-and-swap loop; the carry out of the low half is recovered from the value ATOMS.ADD returns
+  extern __shared__ unsigned int sp_acc[];  // [0, m): low halves, [m, 2m): high halves
   __shared__ int s_bad;
+  unsigned int* acc_lo = sp_acc;
+  unsigned int* acc_hi = sp_acc + m;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   for (int k = blockIdx.x; k < m; k += gridDim.x) {
-    for (int j = k + threadIdx.x; j < m; j += 256) sp_acc[j] = 0;
+    for (int j = k + threadIdx.x; j < m; j += 256) acc_lo[j] = acc_hi[j] = 0u;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     const double sk = cs[k] * kSpFix;
     const int64_t p1 = colptr[k + 1];
-    for (int64_t p = colptr[k] + wq; p < p1; p += 8) {
-      const int i = rowidx[p];
-      const double wi = w[i];
-      const double c = wi * cvals[p] * sk;
-      if (!(fabs(wi) < 1.0e300)) s_bad = 1;  // NaN / Inf weight (benign race: every writer stores 1)
-      if (c != 0.0) {  // rows outside the active mini-batch carry w = 0
-        const int64_t q1 = rowptr[i + 1];
-        for (int64_t q = rowptr[i] + lane; q < q1; q += 32) {
-          const int j = colidx[q];
-          if (j >= k) atomicAdd(reinterpret_cast<unsigned long long*>(&sp_acc[j]),
-                                (unsigned long long)__double2ll_rn(c * (vals[q] * cs[j])));
+    // a warp takes 32 consecutive stored rows of the column at a time: their row index, weight and row extent are fetched
+    // lane-parallel (one round trip for 32 rows instead of three dependent ones per row), then walked with shuffles
+    for (int64_t p0 = colptr[k] + wq * 32; p0 < p1; p0 += 8 * 32) {
+      const int64_t p = p0 + lane;
+      double c = 0.0;
+      int64_t q0 = 0, q1 = 0;
+      if (p < p1) {
+        const int i = rowidx[p];
+        const double wi = w[i];
+        c = wi * cvals[p] * sk;
+        if (!(fabs(wi) < 1.0e300)) s_bad = 1;  // NaN / Inf weight (benign race: every writer stores 1)
+        q0 = rowptr[i];
+        q1 = rowptr[i + 1];
+      }
+      const int nrow = (int)(p1 - p0 < 32 ? p1 - p0 : 32);
+      auto add = [&](int j, double v) {
+        const unsigned long long u = (unsigned long long)__double2ll_rn(v);
+        const unsigned int lo = (unsigned int)u;
+        const unsigned int old = atomicAdd(&acc_lo[j], lo);
+        atomicAdd(&acc_hi[j], (unsigned int)(u >> 32) + ((unsigned int)(old + lo) < lo ? 1u : 0u));
+      };
+      // kSpRows rows per round, up to 64 entries of each in flight before the first is consumed (a row walk is otherwise
+      // a chain of dependent round trips: entries -> column scale -> atomic, twice for a row of 33..64 entries)
+      for (int r = 0; r < nrow; r += kSpRows) {
+        double cr[kSpRows];
+        int64_t b0[kSpRows], b1[kSpRows];
+#pragma unroll
+        for (int h = 0; h < kSpRows; ++h) {
+          const int rr = r + h < nrow ? r + h : r;
+          cr[h] = r + h < nrow ? __shfl_sync(0xffffffffu, c, rr) : 0.0;
+          b0[h] = __shfl_sync(0xffffffffu, q0, rr);
+          b1[h] = cr[h] != 0.0 ? __shfl_sync(0xffffffffu, q1, rr) : b0[h];  // w = 0 (other mini-batch): empty walk
         }
+        int jj[2 * kSpRows];
+        double vv[2 * kSpRows];
+#pragma unroll
+        for (int h = 0; h < kSpRows; ++h)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int64_t q = b0[h] + lane + 32 * u;
+            const bool on = q < b1[h];
+            jj[2 * h + u] = on ? colidx[q] : -1;
+            vv[2 * h + u] = on ? vals[q] : 0.0;
+          }
+        double sc[2 * kSpRows];
+#pragma unroll
+        for (int e = 0; e < 2 * kSpRows; ++e) sc[e] = jj[e] >= k ? cs[jj[e]] : 0.0;
+#pragma unroll
+        for (int e = 0; e < 2 * kSpRows; ++e)
+          if (jj[e] >= k) add(jj[e], cr[e >> 1] * (vv[e] * sc[e]));
+#pragma unroll
+        for (int h = 0; h < kSpRows; ++h)  // rows with more than 64 stored entries
+          for (int64_t q = b0[h] + lane + 64; q < b1[h]; q += 32) {
+            const int j = colidx[q];
+            if (j >= k) add(j, cr[h] * (vals[q] * cs[j]));
+          }
       }
     }
     __syncthreads();
@@ -128,7 +180,8 @@ k_sp_gram(const int64_t* __restrict__ colptr, const int* __restrict__ rowidx, co
     const double ck = cs[k];
     for (int j = k + threadIdx.x; j < m; j += 256) {
       const double den = cs[j] * ck * kSpFix;
-      double g = den > 0.0 ? (double)sp_acc[j] / den : 0.0;
+      const long long acc = (long long)(((unsigned long long)acc_hi[j] << 32) | acc_lo[j]);
+      double g = den > 0.0 ? (double)acc / den : 0.0;
       if (bad) g = __longlong_as_double(0x7ff8000000000000LL);
       out[j] = g;
     }
