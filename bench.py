@@ -340,7 +340,12 @@ def parity_at_scale(S, method, model, reg, hmu, alpha, x0, rank):
     gerr = float(np.max(np.abs(grams["i8"] - grams["dmma"]) / np.outer(d, d)))
     a, b = sols["i8"], sols["dmma"]
     xerr = float(np.linalg.norm(a.x - b.x) / np.linalg.norm(b.x))
-    oerr = float(max(abs(u - v) / abs(v) for u, v in zip(a.obj, b.obj)))
+    oa, ob = np.asarray(a.obj, dtype=np.float64), np.asarray(b.obj, dtype=np.float64)
+    fin = np.isfinite(ob)  # an indbox objective is +Inf while x is outside the box (regularizers.jl:33-39): same pattern, then
+    same_fin = bool(np.array_equal(np.isfinite(oa), fin))  # the finite entries are compared; fval is always finite
+    oerr = float(np.max(np.abs(oa[fin] - ob[fin]) / np.abs(ob[fin]))) if fin.any() else 0.0
+    fa, fb = np.asarray(a.fval, dtype=np.float64), np.asarray(b.fval, dtype=np.float64)
+    oerr = max(oerr, float(np.max(np.abs(fa - fb) / np.abs(fb)))) if same_fin else float("nan")
     same = bool(np.array_equal(a.x != 0, b.x != 0))
     return {"ok": bool(gerr <= 2e-12 and xerr <= 1e-10 and oerr <= 1e-10 and same), "what":
             "k_residues/k_i8syrk/k_crt vs the native fp64 DMMA Gram on the same resident shard, then 3 solver iterations each",

@@ -26,6 +26,9 @@
 //   warp 10    loss warp, for the panels this CTA owns: z_i = sum over ranks in rank order, r_i first (it is on the
 //              critical path) and st.async of r to rs[slot] of every CTA (complete_tx on their rbar[slot]); then the
 //              loss term, w_i and the z / r / w rows to global memory.
+// More than 16 x 256 columns do not fit one cluster: the kernel then covers the LAST 4096 columns (the tensor map, x and
+// gpart are offset by the host) and receives the other columns' contribution to z through z_in (a k_forward pass over
+// them; their share of g is a k_adjoint pass afterwards): 1.5 reads of A per objective + gradient instead of 2.
 // The kernel works on the row window [row_base, row_base + 16*npanels) of the shard (row_base a multiple of 32); rows
 // outside [win_lo, win_hi) get r = w = z = 0 (padding, or rows of another mini-batch).
 // Rotating the owner spreads the exp/log work over the cluster.  No atomics anywhere: per-cluster partial g and
@@ -144,7 +147,8 @@ k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict_
              LossParams lp, int64_t row_base, int64_t win_lo, int64_t win_hi, int64_t npanels, int m,
              double* __restrict__ z_out, double* __restrict__ r_out,
              double* __restrict__ w_out, double* __restrict__ loss_part /* [gridDim.x] */,
-             double* __restrict__ gpart /* [clusters][m] */, long long* __restrict__ prof, int dbg_mode) {
+             double* __restrict__ gpart /* [clusters][m] */, long long* __restrict__ prof, int dbg_mode,
+             const double* __restrict__ z_in /* optional: contribution of columns this launch does not cover (m > 4096) */) {
   const long long k_t0 = PROF ? clock64() : 0;
   long long c_a = 0, c_b = 0, c_c = 0;
   constexpr int S = kFuStages, LAG = kFuLag, NB = kFuBufs;
@@ -367,6 +371,7 @@ k_fused_grad(const __grid_constant__ CUtensorMap amap, const double* __restrict_
           const uint32_t zr = sm_zx + slot * (uint32_t)(kFuMaxCluster * 128) + (uint32_t)(lane * 8);
           double z = lds_f64u(zr);
           for (uint32_t pr = 1; pr < csize; ++pr) z += lds_f64u(zr + pr * 128u);
+          if (z_in) z += z_in[row];
           const bool pad = row < win_lo || row >= win_hi;  // padding rows, or rows of another mini-batch
           const double r = pad ? 0.0 : loss_r_only(lp, z, yv);
           const uint32_t dst = sm_rs + slot * 128u + (uint32_t)(lane * 8), bar = sm_rbar + 8u * slot;

@@ -243,6 +243,7 @@ struct scs_problem {
   int last_stream_path = 0;  // 1 two passes, 2 fused
   bool fu_ready = false, fu_failed = false;
   int fu_cluster = 1, fu_clusters = 0, fu_last_ncl = 0;
+  int64_t fu_col0 = 0;  // m > 4096: the cluster kernel covers columns [fu_col0, m)
   CUtensorMap fumap{};
   double *d_fupart = nullptr, *d_fuloss = nullptr;
   double* d_u = nullptr;  // row vector of the GGN wide branch / A d of the line search (ldd doubles, allocated on first use)
@@ -415,28 +416,30 @@ static void fused_config(scs_problem* p, cudaLaunchConfig_t* cfg, cudaLaunchAttr
 }
 
 // The shape decides the cluster geometry: CTA rank c owns columns [256c, 256c + 256); at most 16 CTAs per cluster.
-static bool fused_shape(const scs_problem* p, int* cluster) {
+// m > 4096: the cluster covers the last 4096 columns [col0, m), the columns before col0 go through k_forward (z) and
+// k_adjoint (g) — 1.5 reads of A per objective + gradient instead of 2 (kernels_fused.cuh).
+static bool fused_shape(const scs_problem* p, int* cluster, int64_t* col0) {
   if (p->loss.kind == SCS_LOSS_QUADFORM || p->sparse) return false;
   if (p->ldd >= (int64_t)1 << 31) return false;  // TMA coordinates are 32-bit
-  const int64_t cl = (p->m + kFuCols - 1) / kFuCols;
-  if (cl > kFuMaxCluster) return false;
-  *cluster = (int)cl;
+  const int64_t cap = (int64_t)kFuMaxCluster * kFuCols;
+  *col0 = p->m > cap ? p->m - cap : 0;
+  *cluster = (int)((p->m - *col0 + kFuCols - 1) / kFuCols);
   return true;
 }
 
 static int fused_setup(scs_problem* p) {
   if (p->fu_ready) return SCS_OK;
   scs_ctx* c = p->ctx;
-  if (!fused_shape(p, &p->fu_cluster)) {
+  if (!fused_shape(p, &p->fu_cluster, &p->fu_col0)) {
     p->fu_failed = true;
-    return fail(SCS_UNSUPPORTED, "fused gradient pass: shape not supported (m > 4096 or quadform loss)");
+    return fail(SCS_UNSUPPORTED, "fused gradient pass: shape not supported (quadform loss or sparse shard)");
   }
   if (!c->encode) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[2] = {(cuuint64_t)p->ldd, (cuuint64_t)p->m};
+  cuuint64_t gdim[2] = {(cuuint64_t)p->ldd, (cuuint64_t)(p->m - p->fu_col0)};
   cuuint64_t gstride[1] = {(cuuint64_t)p->ldd * 8};
   cuuint32_t box[2] = {(cuuint32_t)kFuStageRows, (cuuint32_t)kFuBoxCols};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = c->encode(&p->fumap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->dA, gdim, gstride, box, estr,
+  CUresult r = c->encode(&p->fumap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->dA + p->fu_col0 * p->ldd, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SCS_CUDA_ERROR, "cuTensorMapEncodeTiled (fused pass) failed: " + std::to_string((int)r));
@@ -461,6 +464,7 @@ static int fused_setup(scs_problem* p) {
   p->fu_clusters = ncl;
   SCS_TRY(dalloc(&p->d_fupart, (size_t)ncl * p->m));
   SCS_TRY(dalloc(&p->d_fuloss, (size_t)ncl * p->fu_cluster));
+  if (p->fu_col0 > 0 && !p->d_u) SCS_TRY(dalloc(&p->d_u, p->ldd));
   p->fu_ready = true;
   return SCS_OK;
 }
@@ -468,7 +472,8 @@ static int fused_setup(scs_problem* p) {
 static bool fused_wanted(scs_problem* p) {
   if (p->stream_mode == 1 || p->fu_failed) return false;
   int cl;
-  if (p->stream_mode == 0 && !p->fu_ready && !fused_shape(p, &cl)) return false;
+  int64_t c0;
+  if (p->stream_mode == 0 && !p->fu_ready && !fused_shape(p, &cl, &c0)) return false;
   return true;
 }
 
@@ -483,6 +488,21 @@ static int run_fused(scs_problem* p, const double* dx, int wk, bool reduce = tru
   lp.weight_kind = wk;
   const int64_t npanels = (p->ahi - p->alo) / kFuRows;
   const int ncl = (int)std::max<int64_t>(1, std::min<int64_t>(p->fu_clusters, (npanels + 1) / 2));
+  const int64_t col0 = p->fu_col0;
+  const int mf = (int)(p->m - col0);  // columns the cluster kernel covers
+  const double* zin = nullptr;
+  const int64_t nproc = p->ahi - p->alo;
+  if (col0 > 0) {  // z1 = A[:, :col0] x[:col0] for the rows of the window (rows outside it come out as 0)
+    LossParams lz = p->loss;
+    lz.kind = 2;
+    lz.weight_kind = 0;
+    const int64_t blocks = (nproc + kFwdRows - 1) / kFwdRows;
+    if (blocks > 0)
+      LAUNCH(c, k_forward<8>, (unsigned)blocks, kFwdThreads, 0, p->dA + p->alo, p->ldd, nproc, p->win_lo - p->alo,
+             p->win_hi - p->alo, (int)col0, dx, p->dy + p->alo, lz, p->d_u + p->alo, (double*)nullptr, (double*)nullptr,
+             p->d_losspart);
+    zin = p->d_u;
+  }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fused_config(p, &cfg, attr, ncl);
@@ -492,8 +512,9 @@ static int run_fused(scs_problem* p, const double* dx, int wk, bool reduce = tru
     const size_t np = (size_t)cfg.gridDim.x * 8;
     CU_TRY(cudaMalloc((void**)&dprof, np * sizeof(long long)));
     CU_TRY(cudaMemsetAsync(dprof, 0, np * sizeof(long long), c->stream));
-    le = cudaLaunchKernelEx(&cfg, k_fused_grad<true>, p->fumap, dx, (const double*)p->dy, lp, p->alo, p->win_lo,
-                            p->win_hi, npanels, (int)p->m, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, dprof, atoi(getenv("SCS_FUSED_PROF")) == 2 ? 1 : 0);
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<true>, p->fumap, dx + col0, (const double*)p->dy, lp, p->alo, p->win_lo,
+                            p->win_hi, npanels, mf, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart, dprof,
+                            atoi(getenv("SCS_FUSED_PROF")) == 2 ? 1 : 0, zin);
     std::vector<long long> h(np);
     cudaMemcpyAsync(h.data(), dprof, np * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -509,15 +530,23 @@ static int run_fused(scs_problem* p, const double* dx, int wk, bool reduce = tru
             ncl, p->fu_cluster, panels, s[0] / nb, s[0] / nb / panels, s[1] / nb, s[2] / nb, s[7] / nb, s[3] / nb,
             s[4] / nb, s[5] / nb, s[6] / nb);
   } else {
-    le = cudaLaunchKernelEx(&cfg, k_fused_grad<false>, p->fumap, dx, (const double*)p->dy, lp, p->alo, p->win_lo,
-                            p->win_hi, npanels, (int)p->m, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart,
-                            (long long*)nullptr, 0);
+    le = cudaLaunchKernelEx(&cfg, k_fused_grad<false>, p->fumap, dx + col0, (const double*)p->dy, lp, p->alo, p->win_lo,
+                            p->win_hi, npanels, mf, p->dz, p->dr, p->dw, p->d_fuloss, p->d_fupart,
+                            (long long*)nullptr, 0, zin);
   }
   c->launches += 1;
   if (le != cudaSuccess) return fail(SCS_CUDA_ERROR, std::string("k_fused_grad launch: ") + cudaGetErrorString(le));
   p->fu_last_ncl = ncl;
+  if (col0 > 0) {  // g[:col0] = A[:, :col0]' r
+    const int64_t blocks = (nproc + 64 * 8 - 1) / (64 * 8);
+    if (blocks > 0)
+      LAUNCH(c, k_adjoint<8>, (unsigned)blocks, kAdjThreads, 0, p->dA + p->alo, p->ldd, nproc, (int)col0,
+             (const double*)(p->dr + p->alo), p->d_adjpart);
+    LAUNCH(c, k_colsum, (unsigned)((col0 + 31) / 32), 256, 0, p->d_adjpart, blocks, (int)col0, p->d_gl);
+    reduce = true;  // the caller's kernel only knows the single-launch layout
+  }
   if (reduce) {
-    LAUNCH(c, k_colsum, (unsigned)((p->m + 31) / 32), 256, 0, p->d_fupart, (int64_t)ncl, (int)p->m, p->d_gl);
+    LAUNCH(c, k_colsum, (unsigned)((mf + 31) / 32), 256, 0, p->d_fupart, (int64_t)ncl, mf, p->d_gl + col0);
     LAUNCH(c, k_sum_partials, 1, kVecThreads, 0, p->d_fuloss, (int64_t)ncl * p->fu_cluster, p->d_gl + p->m);
   }
   p->last_stream_path = 2;
@@ -956,7 +985,8 @@ static int run_gram_i8(scs_problem* p, int* done) {
   // travels slab by slab: the CRT of slab s+1 runs on the main stream while NCCL reduces slab s on the second stream.
   // Slab boundaries split the packed triangle into equal byte counts (rows ~ sqrt).
   if (!p->d_Gpack) SCS_TRY(dalloc(&p->d_Gpack, (size_t)m * (m + 1) / 2));
-  const int nslab = m >= 2048 ? 4 : 1;
+  static const int slab_env = getenv("SCS_GRAM_SLABS") ? atoi(getenv("SCS_GRAM_SLABS")) : 0;  // tuning switch (1..4)
+  const int nslab = m >= 2048 ? (slab_env >= 1 && slab_env <= 4 ? slab_env : 4) : 1;
   int j0 = 0;
   for (int sidx = 0; sidx < nslab; ++sidx) {
     int j1 = sidx == nslab - 1 ? m : (int)std::floor(m * std::sqrt((sidx + 1.0) / nslab));
@@ -2409,7 +2439,7 @@ static int step_device(scs_problem* p, XRef x, XRef xprev, int64_t iter, double*
   // second gradient at x⁺ (prox-L-BFGS-SCORE.jl:148-150); it is next iteration's ∇q, and its loss value is next
   // epoch's objective, so neither is recomputed
   XRef xn{xnew, xnew_id};
-  const bool fold = c->world == 1 && fused_wanted(p) && !(p->fwd_id == xn.id);
+  const bool fold = c->world == 1 && fused_wanted(p) && !(p->fwd_id == xn.id) && p->m <= (int64_t)kFuMaxCluster * kFuCols;
   int folded = 0;
   if (fold) {
     int rc = run_fused(p, xn.d, SCS_WEIGHTS_NEWTON, /*reduce=*/false);

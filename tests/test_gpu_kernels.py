@@ -79,15 +79,39 @@ def test_fused_gradient_geometries(scs, n, m):
     p.close()
 
 
-def test_fused_unsupported_shape_is_rejected_or_falls_back(scs):
-    n, m = 64, 4100  # wider than 16 CTAs x 256 columns
-    A, y, x = logistic_problem(n, m)
-    p = scs.Problem(A, y, x, scs.LogisticLoss(1 / n), 0.1)
-    fv, g, *_ = p.loss_eval(x)  # auto: two passes
-    assert p.stream_path() == "two_pass"
-    p.set_stream_mode("fused")
-    with pytest.raises(scs.UnsupportedError):
-        p.loss_eval(2 * x)
+@pytest.mark.parametrize("n,m", [(64, 4100), (700, 6000), (1030, 8192), (333, 9000)])
+@pytest.mark.parametrize("loss", ["logistic_consistent", "ls"])
+def test_fused_gradient_wider_than_one_cluster(scs, n, m, loss):
+    """m > 16 x 256 columns: the cluster kernel covers the last 4096 columns and receives z of the others from a k_forward
+    pass (z_in), their share of g comes from a k_adjoint pass: 1.5 reads of A.  Same loss, z, r, w, g as the oracle and as
+    the two-pass kernels, window masking included."""
+    A = synth.make_A(n, m, seed=5)
+    x = synth.make_x0(m, seed=6) * 0.2
+    if loss == "ls":
+        y = synth.make_targets_ls(A @ synth.make_x_true(m, seed=7), seed=8)
+        Lo, Lg = O.LeastSquaresLoss(float(n)), scs.LeastSquaresLoss(float(n))
+    else:
+        y = synth.make_labels_logistic(A @ synth.make_x_true(m, seed=7, frac=0.1), seed=8)
+        Lo, Lg = O.LogisticLoss(1 / n, "consistent"), scs.LogisticLoss(1 / n, "consistent")
+    p = scs.Problem(A, y, x, Lg, 0.1)
+    for lo, hi in ((0, n), (n // 4 + 1, n - 3)):
+        p.set_active_rows(lo, hi)
+        out = {}
+        for mode in ("fused", "two_pass"):
+            p.set_stream_mode(mode)
+            p.loss_eval(0.3 * x, weights="ggn")  # evict the cached pass
+            out[mode] = p.loss_eval(x, weights="ggn", want_rows=True)
+            assert p.stream_path() == mode
+        fv, g, zg, rg, wg = out["fused"]
+        As, ys = A[lo:hi], y[lo:hi]
+        z = As @ x
+        r, w = Lo.ggn_weights(z, ys)
+        assert relerr(zg[lo:hi], z) <= 1e-13 and np.all(zg[hi:] == 0)
+        assert abs(fv - Lo.f(As, ys, x)) <= 1e-13 * abs(Lo.f(As, ys, x))
+        np.testing.assert_allclose(rg[lo:hi], r, rtol=1e-11, atol=1e-300)
+        assert relerr(g, As.T @ r) <= 1e-12
+        fv2, g2, *_ = out["two_pass"]
+        assert abs(fv - fv2) <= 1e-13 * abs(fv2) and relerr(g, g2) <= 1e-12
     p.close()
 
 
