@@ -881,6 +881,83 @@ k_i8syrk2(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
   }
 }
 
+// ---- all-reduce of the packed Gram over NVLink peer memory (one node, one process per GPU) ---------------------------
+// Every rank's packed triangle lives in an allocation the other ranks have mapped (cudaIpc); the exchange step is three
+// small kernels of our own instead of an NCCL call:
+//   k_p2p_barrier        everybody's triangle is complete (stream order locally, flags across ranks)
+//   k_p2p_reduce_scatter rank r sums slice r of all ranks' triangles — loads straight from peer HBM over NVLink, always in
+//                        rank order 0..W-1 — and writes the result into its own copy
+//   k_p2p_barrier, k_p2p_allgather (every rank copies the other W-1 reduced slices), k_p2p_barrier
+// Each entry is reduced exactly once, by one rank, in a fixed order: all ranks end with bitwise the same matrix (the
+// replicated solve depends on that) and the result does not depend on timing.  Flags: receiver-owned, one 64-bit slot
+// per sender, monotonically increasing epochs; system-scope release / acquire; bounded spins (a dead peer traps the
+// kernel instead of hanging the device).
+constexpr int kP2PMaxWorld = 16;
+struct P2PPeers {
+  double* base[kP2PMaxWorld];               // rank r's buffer as mapped in this process (own buffer for r == rank)
+  unsigned long long* flags[kP2PMaxWorld];  // rank r's flag slots (receiver-owned: flags[r][sender])
+};
+__global__ void __launch_bounds__(32) k_p2p_barrier(P2PPeers pp, int rank, int world, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  __threadfence_system();
+  if (r < world && r != rank)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flags[r] + rank), "l"(epoch) : "memory");
+  if (r < world && r != rank) {
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pp.flags[rank] + r) : "memory");
+      if (seen >= epoch) break;
+      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer is gone
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+// this rank's slice of [0, count): [count * rank / world, count * (rank + 1) / world) rounded to even offsets
+SCS_DEVINL void p2p_slice(size_t count, int r, int world, size_t& lo, size_t& hi) {
+  lo = (count * (size_t)r / (size_t)world) & ~(size_t)1;
+  hi = r == world - 1 ? count : (count * (size_t)(r + 1) / (size_t)world) & ~(size_t)1;
+}
+__global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PPeers pp, int rank, int world, size_t count) {
+  size_t lo, hi;
+  p2p_slice(count, rank, world, lo, hi);
+  const size_t npair = (hi - lo) / 2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < npair; i += (size_t)gridDim.x * 256) {
+    const size_t e = lo + 2 * i;
+    double2 v[kP2PMaxWorld];  // all peers' loads in flight before the first add (a remote load is a few microseconds)
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < world) v[r] = __ldcg(reinterpret_cast<const double2*>(pp.base[r] + e));
+    double2 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < kP2PMaxWorld; ++r)
+      if (r < world) {  // rank order: the same sum on every run
+        acc.x += v[r].x;
+        acc.y += v[r].y;
+      }
+    *reinterpret_cast<double2*>(pp.base[rank] + e) = acc;
+  }
+  if (((hi - lo) & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail (last slice only)
+    const size_t e = hi - 1;
+    double acc = __ldcg(pp.base[0] + e);
+    for (int r = 1; r < world; ++r) acc += __ldcg(pp.base[r] + e);
+    pp.base[rank][e] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_p2p_allgather(P2PPeers pp, int rank, int world, size_t count) {
+  // blockIdx.y = which peer's slice (skipping this rank's own)
+  const int r = (int)blockIdx.y >= rank ? (int)blockIdx.y + 1 : (int)blockIdx.y;
+  size_t lo, hi;
+  p2p_slice(count, r, world, lo, hi);
+  const size_t npair = (hi - lo) / 2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < npair; i += (size_t)gridDim.x * 256) {
+    const size_t e = lo + 2 * i;
+    *reinterpret_cast<double2*>(pp.base[rank] + e) = __ldcg(reinterpret_cast<const double2*>(pp.base[r] + e));
+  }
+  if (((hi - lo) & 1) && blockIdx.x == 0 && threadIdx.x == 0) pp.base[rank][hi - 1] = __ldcg(pp.base[r] + hi - 1);
+}
+
 // ---- int8 tensor-pipe peak (measurement aid for bench.py: the denominator of k_i8syrk's roofline) -----------------
 // One CTA per SM issues the SAME 128x256x32 kind::i8 UMMA k_i8syrk issues, back to back, on operands that never leave
 // shared memory: no TMA, no epilogue, no global traffic — what the tensor pipe sustains at the clock the power cap allows

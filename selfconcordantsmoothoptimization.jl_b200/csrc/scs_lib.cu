@@ -222,6 +222,11 @@ struct scs_problem {
   // signed weights: compacted planes of the minority-sign rows (i8_setup_signed), per-block statistics
   int8_t* d_cplanes = nullptr;
   double* d_Gpack = nullptr;  // several ranks: packed upper triangle of the Gram, what the all-reduce moves
+  // own all-reduce over NVLink peer memory (k_p2p_*): d_Gpack is then an IPC-shared allocation [count | flag slots]
+  bool p2p_tried = false, p2p_ok = false;
+  P2PPeers p2p{};
+  void* p2p_opened[kP2PMaxWorld] = {nullptr};
+  unsigned long long p2p_epoch = 0;
   int64_t ldc = 0, i8_ccount = 0;
   int64_t* d_negbase = nullptr;
   double* d_wpart = nullptr;
@@ -887,6 +892,81 @@ static int i8_launch_syrk(scs_problem* p, const CUtensorMap& amap, const CUtenso
   return SCS_OK;
 }
 
+// Maps every rank's packed-Gram buffer into every process (cudaIpc) so that the exchange step can be our own kernels
+// over NVLink instead of an NCCL call.  One-time, collective; if any rank cannot do it (no peer access, IPC not
+// permitted in this container, SCS_P2P=0) every rank stays on NCCL.
+static int p2p_setup(scs_problem* p, size_t count) {
+  scs_ctx* c = p->ctx;
+  if (p->p2p_tried) return SCS_OK;
+  p->p2p_tried = true;
+  const int W = c->world;
+  static const bool disabled = getenv("SCS_P2P") && atoi(getenv("SCS_P2P")) == 0;
+  bool ok = !disabled && W <= kP2PMaxWorld;
+  double* base = nullptr;
+  const size_t bytes = count * sizeof(double) + 4096;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    ok = cudaMalloc((void**)&base, bytes) == cudaSuccess && cudaMemset(base, 0, bytes) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
+    cudaGetLastError();
+  }
+  // exchange the 64-byte handles: one value per byte in a zero-filled [W x 64] table of doubles, summed by the all-reduce
+  // (every slot has exactly one non-zero contributor, so the sum is exact)
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  std::vector<double> tab((size_t)W * (hb + 1), 0.0);
+  if (ok) {
+    const unsigned char* hbytes = reinterpret_cast<const unsigned char*>(&mine);
+    for (size_t i = 0; i < hb; ++i) tab[(size_t)c->rank * (hb + 1) + i] = (double)hbytes[i];
+    tab[(size_t)c->rank * (hb + 1) + hb] = 1.0;  // "I have a handle"
+  }
+  double* dtab = nullptr;
+  CU_TRY(cudaMalloc((void**)&dtab, tab.size() * sizeof(double)));
+  CU_TRY(cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int rc = allreduce(c, dtab, tab.size());
+  if (rc == SCS_OK) {
+    cudaMemcpyAsync(tab.data(), dtab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(dtab);
+  SCS_TRY(rc);
+  for (int r = 0; r < W && ok; ++r) ok = tab[(size_t)r * (hb + 1) + hb] == 1.0;
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == c->rank) {
+        p->p2p.base[r] = base;
+      } else {
+        cudaIpcMemHandle_t h;
+        unsigned char* hbytes = reinterpret_cast<unsigned char*>(&h);
+        for (size_t i = 0; i < hb; ++i) hbytes[i] = (unsigned char)(tab[(size_t)r * (hb + 1) + i] + 0.5);
+        void* ptr = nullptr;
+        ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        cudaGetLastError();
+        p->p2p_opened[r] = ok ? ptr : nullptr;
+        p->p2p.base[r] = (double*)ptr;
+      }
+      if (ok) p->p2p.flags[r] = reinterpret_cast<unsigned long long*>(p->p2p.base[r] + count);
+    }
+  }
+  bool all_ok = false;
+  SCS_TRY(agree_ok(c, ok, &all_ok));
+  if (!all_ok) {
+    for (int r = 0; r < W; ++r)
+      if (p->p2p_opened[r]) {
+        cudaIpcCloseMemHandle(p->p2p_opened[r]);
+        p->p2p_opened[r] = nullptr;
+      }
+    if (base) cudaFree(base);
+    if (c->rank == 0 && !disabled)
+      fprintf(stderr, "[scs_b200] peer-memory all-reduce unavailable (cudaIpc / peer access): the Gram exchange uses NCCL\n");
+    return SCS_OK;
+  }
+  dfree(p->d_Gpack);
+  p->d_Gpack = base;
+  p->p2p_ok = true;
+  return SCS_OK;
+}
+
 // returns *done = 0 when this call cannot be served (non-finite weights, or no memory for the compacted planes of a
 // signed Gram): the caller then runs the DMMA kernel
 static int run_gram_i8(scs_problem* p, int* done) {
@@ -984,7 +1064,35 @@ static int run_gram_i8(scs_problem* p, int* done) {
   // Several ranks: the exchange step.  Only the packed upper triangle travels (half the bytes of the square), and it
   // travels slab by slab: the CRT of slab s+1 runs on the main stream while NCCL reduces slab s on the second stream.
   // Slab boundaries split the packed triangle into equal byte counts (rows ~ sqrt).
-  if (!p->d_Gpack) SCS_TRY(dalloc(&p->d_Gpack, (size_t)m * (m + 1) / 2));
+  const size_t npack = (size_t)m * (m + 1) / 2;
+  SCS_TRY(p2p_setup(p, npack));
+  if (p->p2p_ok) {
+    // the exchange step as our own kernels over NVLink peer memory (kernels_i8gram.cuh: k_p2p_*)
+    {
+      StageTimer t(c, ST_GRAMFIN);
+      LAUNCH(c, k_crt, dim3((m + 255) / 256, (m + 3) / 4), 256, 0, p->d_i8partial, pl, (const double*)p->d_colinv,
+             (const double*)p->d_wstat, nonneg ? 1 : 0, p->d_G, 0, m, p->d_Gpack);
+    }
+    {
+      StageTimer t(c, ST_COMM);
+      const int W = c->world;
+      const unsigned gx = (unsigned)std::min<size_t>(4 * (size_t)c->num_sms, (npack / W / 2 + 255) / 256 + 1);
+      LAUNCH(c, k_p2p_barrier, 1, 32, 0, p->p2p, c->rank, W, ++p->p2p_epoch);
+      LAUNCH(c, k_p2p_reduce_scatter, gx, 256, 0, p->p2p, c->rank, W, npack);
+      LAUNCH(c, k_p2p_barrier, 1, 32, 0, p->p2p, c->rank, W, ++p->p2p_epoch);
+      LAUNCH(c, k_p2p_allgather, dim3(std::max(1u, gx / (unsigned)(W - 1)), (unsigned)(W - 1)), 256, 0, p->p2p, c->rank, W,
+             npack);
+      LAUNCH(c, k_p2p_barrier, 1, 32, 0, p->p2p, c->rank, W, ++p->p2p_epoch);
+    }
+    {
+      StageTimer t(c, ST_GRAMFIN);
+      const int t32 = (m + 31) / 32;
+      LAUNCH(c, k_unpack_upper, t32 * (t32 + 1) / 2, 256, 0, (const double*)p->d_Gpack, m, p->d_G);
+    }
+    *done = 2;
+    return SCS_OK;
+  }
+  if (!p->d_Gpack) SCS_TRY(dalloc(&p->d_Gpack, npack));
   static const int slab_env = getenv("SCS_GRAM_SLABS") ? atoi(getenv("SCS_GRAM_SLABS")) : 0;  // tuning switch (1..4)
   const int nslab = m >= 2048 ? (slab_env >= 1 && slab_env <= 4 ? slab_env : 4) : 1;
   int j0 = 0;
@@ -1638,6 +1746,8 @@ extern "C" int scs_problem_destroy(scs_problem* p) {
   if (!p) return SCS_OK;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
+  for (int r = 0; r < kP2PMaxWorld; ++r)
+    if (p->p2p_opened[r]) cudaIpcCloseMemHandle(p->p2p_opened[r]);
   void* bufs[] = {p->dA,      p->dy,      p->dz,     p->dr,      p->dw,       p->vx[0],   p->vx[1],    p->vx[2],
                   p->d_gl,    p->d_gr,    p->d_hr,   p->d_rhs,   p->d_sol,    p->d_d,     p->d_dx,     p->d_delta,
                   p->d_gq,    p->d_gqprev, p->d_gamma, p->d_q,   p->d_t1,     p->d_t2,    p->d_xstar,  p->d_trial,
