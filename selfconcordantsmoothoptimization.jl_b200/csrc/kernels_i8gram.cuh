@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(32) k_p2p_barrier(P2PPeers pp, int rank, int w
       unsigned long long seen;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pp.flags[rank] + r) : "memory");
       if (seen >= epoch) break;
-      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer is gone
+      if (clock64() - t0 > 120000000000LL) __trap();  // ~60 s: a peer is gone
     }
   }
   __syncwarp();
