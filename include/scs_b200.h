@@ -94,8 +94,8 @@ int scs_problem_create(scs_ctx* ctx, const double* A_colmajor, int64_t n_local, 
 /* The same from a compressed-sparse-column shard (Julia SparseMatrixCSC{Float64,Int64}: colptr (m+1), rowval, nzval;
  * index_base 1 for Julia, 0 for scipy).  Only the stored entries cross PCIe.  storage: 1 = expand on the device into the
  * dense resident layout (dense kernels: HBM-roofline passes, tensor-core Gram); 2 = keep the shard sparse (CSR + CSC
- * copies; k_sp_forward / k_sp_adjoint / k_sp_gram, ~12 bytes per stored entry and pass; no int8 Gram, no GGN
- * underdetermined branch, no scs_problem_read_rows); 0 = sparse when fewer than 4 % of the entries are stored.
+ * copies; k_sp_forward / k_sp_adjoint / k_sp_gram, ~12 bytes per stored entry and pass; no int8 Gram, no
+ * scs_problem_read_rows); 0 = sparse when fewer than 4 % of the entries are stored.
  * scs_problem_is_sparse reports which one was taken.  scs_get_gram_path returns 3 for the sparse Gram. */
 int scs_problem_create_csc(scs_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                            int64_t index_base, int64_t n_local, int64_t m, const double* y, int loss_kind,
@@ -125,9 +125,10 @@ int scs_set_smoother(scs_problem* p, int smoother_kind, double mu, const double*
                      const double* ub, int64_t nub);
 int scs_set_method(scs_problem* p, int method_kind, int ss_type, int use_prox, int lbfgs_m);
 int scs_set_L(scs_problem* p, int has_L, double L);
-/* Gram kernel selection: 0 = auto (tcgen05 int8 emulated-fp64 path when the weights are non-negative and the shard
- * is large, DMMA otherwise), 1 = always DMMA.8x8x4, 2 = tcgen05 int8 whenever the weights are non-negative.
- * scs_get_gram_path reports what the last Gram used (1 = DMMA, 2 = tcgen05 int8). */
+/* Gram kernel selection: 0 = auto (tcgen05 int8 emulated-fp64 path when the shard is large — m >= 512, >= 32768 active
+ * rows — and its residue planes fit in HBM, DMMA otherwise), 1 = always DMMA.8x8x4, 2 = tcgen05 int8 whenever possible.
+ * The int8 path serves weights of either sign (scs_get_gram_signed); only non-finite weights fall back to DMMA, which
+ * propagates them.  scs_get_gram_path reports what the last Gram used (1 = DMMA, 2 = tcgen05 int8, 3 = sparse). */
 int scs_set_gram_mode(scs_problem* p, int mode);
 int scs_get_gram_path(scs_problem* p, int* path);
 /* Fixed-point precision of the emulated-fp64 Gram.  The columns of diag(sqrt w) A are scaled to a common 2-norm T before
