@@ -996,12 +996,17 @@ static int run_gram_i8(scs_problem* p, int* done) {
       double st[WS_COUNT];
       CU_TRY(cudaMemcpyAsync(st, p->d_wstat, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
       CU_TRY(cudaStreamSynchronize(c->stream));
-      if (st[WS_BAD] != 0.0) return SCS_OK;  // NaN / Inf weights: the fp64 kernel propagates them
-      const int64_t nneg = (int64_t)(st[WS_NNEG] + 0.5);
+      // NaN / Inf weights: one GPU hands the call to the fp64 kernel, which propagates them; with several ranks every
+      // rank must stay on the same exchange path, so the int8 path goes on and k_crt poisons the result (WS_BAD)
+      const bool bad = st[WS_BAD] != 0.0;
+      if (bad && c->world == 1) return SCS_OK;
+      const int64_t nneg = bad ? 0 : (int64_t)(st[WS_NNEG] + 0.5);
+      int rc = nneg > 0 ? i8_setup_signed(p) : SCS_OK;
+      if (rc != SCS_OK && rc != SCS_OOM) return rc;
+      bool all_ok = rc == SCS_OK;
+      if (c->world > 1) SCS_TRY(agree_ok(c, rc == SCS_OK, &all_ok));  // every rank takes the same Gram path
+      if (!all_ok) return SCS_OK;  // no room for the compacted planes somewhere: all ranks fall back to DMMA together
       if (nneg > 0) {
-        int rc = i8_setup_signed(p);
-        if (rc == SCS_OOM) return SCS_OK;
-        SCS_TRY(rc);
         p->i8_signed = true;
         p->i8_minor_neg = nneg <= nproc - nneg;
         p->i8_ccount = p->i8_minor_neg ? nneg : nproc - nneg;

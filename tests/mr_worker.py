@@ -46,6 +46,20 @@ def _gram_exchange_checks(ctx, rank, world):
         assert all(torch.equal(lst[0], u) for u in lst), mode
         worst = max(worst, err)
     model.close()
+    # weights of both signs (the literal +-1 cross-entropy pair): every rank compacts its own minority rows, the signed
+    # integer Grams are reconstructed per rank and summed by the same exchange step
+    wl = O.LogisticLoss(1 / n).ggn_weights(A @ x, y)[1]
+    assert np.any(wl < 0)
+    Gl = A.T @ (wl[:, None] * A)
+    dl = np.sqrt(np.diag(A.T @ (np.abs(wl)[:, None] * A)))
+    model = S.Problem(A[r0:r0 + nl], y[r0:r0 + nl], x, S.LogisticLoss(1 / n, "literal"), 1e-2, ctx=ctx)
+    model.set_gram_mode("i8")
+    G = model.gram(x, weights="ggn")
+    assert model.gram_path() == "i8" and model.gram_signed()[0] > 0
+    err = float(np.max(np.abs(G - Gl) / np.outer(dl, dl)))
+    assert err <= 2e-12, ("signed", rank, err)
+    worst = max(worst, err)
+    model.close()
     return worst
 
 
