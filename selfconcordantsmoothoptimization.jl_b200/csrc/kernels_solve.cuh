@@ -195,9 +195,12 @@ SCS_DEVINL void load_tile_T(double* dst, const double* __restrict__ M, int64_t l
 // right-hand side below the block: b_i -= sum_c L[i, k0+c] y_c (128 rows each).  128 threads.
 // tile0: first triangular tile index handled by CTA 0 (the look-ahead sequence passes 1: the diagonal tile right below
 // the panel belongs to k_chol_diag).
+// kpan: 64-column panels applied in one read-modify-write of the tile, ending with panel k0 (2 = panels k0 - 64 and k0:
+// the paired sequence, which halves the passes over the trailing matrix).  colonly: the tiles are those of the first
+// block column only (tile index = block row).
 __global__ void __launch_bounds__(128, 3) k_syrk_update(double* __restrict__ M, int64_t ld, int m, int k0, int ntiles,
                                                      double* __restrict__ bvec, const double* __restrict__ yvec,
-                                                     int tile0) {
+                                                     int tile0, int kpan, int colonly) {
   extern __shared__ double tile_sh[];
   double* As = tile_sh;
   double* Bs = tile_sh + kNB * kTS;
@@ -225,7 +228,10 @@ __global__ void __launch_bounds__(128, 3) k_syrk_update(double* __restrict__ M, 
     return;
   }
   int ti, tj;
-  {
+  if (colonly) {
+    ti = blockIdx.x + tile0;
+    tj = 0;
+  } else {
     const int tt = blockIdx.x + tile0;
     int r = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
     while ((r + 1) * (r + 2) / 2 <= tt) ++r;
@@ -234,17 +240,19 @@ __global__ void __launch_bounds__(128, 3) k_syrk_update(double* __restrict__ M, 
     tj = tt - r * (r + 1) / 2;
   }
   const int r0 = base + ti * kNB, c0 = base + tj * kNB;
-  load_tile_T(As, M, ld, m, k0, r0, nb, tid);
-  if (ti == tj) {
-    Bs = As;  // diagonal tile: both operands are the same panel rows
-  } else {
-    load_tile_T(Bs, M, ld, m, k0, c0, nb, tid);
-  }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
   double acc[4][4][2] = {};
-  tile_mma_64(As, Bs, wm, wn, g, t, acc);
+  if (ti == tj) Bs = As;  // diagonal tile: both operands are the same panel rows
+#pragma unroll 1
+  for (int h = kpan - 1; h >= 0; --h) {  // earlier panels are full (only the last block of the matrix can be short)
+    const int kc = k0 - h * kNB, kn = h ? kNB : nb;
+    if (h != kpan - 1) __syncthreads();
+    load_tile_T(As, M, ld, m, kc, r0, kn, tid);
+    if (ti != tj) load_tile_T(Bs, M, ld, m, kc, c0, kn, tid);
+    __syncthreads();
+    tile_mma_64(As, Bs, wm, wn, g, t, acc);
+  }
   // read-modify-write in four batches of eight independent loads: the batch latency hides behind the other resident
   // CTAs (keeping all 32 old values in registers across the MMAs cost a third CTA per SM: 230 -> ~170 registers)
 #pragma unroll
@@ -281,18 +289,21 @@ __global__ void __launch_bounds__(128, 3) k_syrk_update(double* __restrict__ M, 
 //                     (L_kk broadcast from shared memory), and b_i -= L21[i,:] y_k for the rows below.
 //   k_syrk_update(k): A22 -= L21 L21' for all lower tiles except the first diagonal one (tile0 = 1).
 constexpr int kCholDiagThreads = 256;
-constexpr int kCholDiagSmem = (kNB * kLS + kNB * kTS + 4 * kNB) * 8;
+constexpr int kCholDiagSmem = (kNB * kLS + 2 * kNB * kTS + 4 * kNB) * 8;
 #define SCS_STAMP(i)                                     \
   do {                                                   \
     if (prof != nullptr && tid == 0) prof[i] = clock64(); \
   } while (0)
 __global__ void __launch_bounds__(kCholDiagThreads)
 k_chol_diag(double* __restrict__ M, int64_t ld, int m, int k0, double* __restrict__ rdiag_g, int* __restrict__ info,
-            const double* __restrict__ bvec, double* __restrict__ yvec, long long* __restrict__ prof) {
+            const double* __restrict__ bvec, double* __restrict__ yvec, long long* __restrict__ prof, int nprev) {
+  // nprev: previous panels whose update of this tile is still pending (0 for the first block, 1 in the plain
+  // look-ahead sequence, 2 at the pair boundaries of the paired sequence)
   extern __shared__ double dsh[];
   double* D = dsh;                 // the tile, D[r][c] (row stride kLS); the factor on exit
   double* As = D + kNB * kLS;      // phase 0: As[p][i] = L[k0+i, k0-64+p]; phase 1: Ps[k][r] = panel column k, row r
-  double* rds = As + kNB * kTS;    // 1 / L_jj
+  double* As2 = As + kNB * kTS;    // phase 0, nprev = 2: As2[p][i] = L[k0+i, k0-128+p]
+  double* rds = As2 + kNB * kTS;   // 1 / L_jj
   double* bk = rds + kNB;          // right-hand side of this block, updated panel by panel
   double* ys = bk + kNB;           // y_k
   const int nb = min(kNB, m - k0);
@@ -302,12 +313,13 @@ k_chol_diag(double* __restrict__ M, int64_t ld, int m, int k0, double* __restric
   // every thread has its 16 entries of the tile and its 16 entries of the panel rows in flight before the first store.
   {
     const int i = tid & 63, pq = tid >> 6;
-    double vd[16], va[16];
+    double vd[16], va[16], va2[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int c = pq + 4 * u;
       vd[u] = (i < nb && c <= i) ? M[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
-      va[u] = (k0 > 0 && i < nb) ? M[(int64_t)(k0 - kNB + c) * ld + k0 + i] : 0.0;
+      va[u] = (nprev >= 1 && i < nb) ? M[(int64_t)(k0 - kNB + c) * ld + k0 + i] : 0.0;
+      va2[u] = (nprev >= 2 && i < nb) ? M[(int64_t)(k0 - 2 * kNB + c) * ld + k0 + i] : 0.0;
     }
     if (tid >= 192) bk[tid - 192] = (tid - 192) < nb ? bvec[k0 + tid - 192] : 0.0;
 #pragma unroll
@@ -315,14 +327,16 @@ k_chol_diag(double* __restrict__ M, int64_t ld, int m, int k0, double* __restric
       const int c = pq + 4 * u;
       D[i * kLS + c] = vd[u];
       As[c * kTS + i] = va[u];
+      if (nprev >= 2) As2[c * kTS + i] = va2[u];
     }
   }
   __syncthreads();
   SCS_STAMP(1);
-  if (k0 > 0) {  // D -= L(k,k-1) L(k,k-1)': 4 warps x (32x32), 8 shared-memory loads per 16 DMMAs
+  if (nprev >= 1) {  // D -= L(k,k-1) L(k,k-1)' (and the panel before): 4 warps x (32x32), 8 LDS per 16 DMMAs
     if (tid < 128) {
       const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
       double acc[4][4][2] = {};
+      if (nprev >= 2) tile_mma_64(As2, As2, wm, wn, g, t, acc);
       tile_mma_64(As, As, wm, wn, g, t, acc);
 #pragma unroll
       for (int i = 0; i < 4; ++i)

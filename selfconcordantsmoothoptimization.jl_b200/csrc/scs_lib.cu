@@ -69,6 +69,8 @@ struct scs_ctx {
   cudaEvent_t ev_trsm[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
   cudaEvent_t ev_slab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // slab-pipelined Gram all-reduce
   int solve_mode = 0;  // 0 = look-ahead sequence, 1 = k_panel / k_syrk_update sequence (SCS_SOLVE_LEGACY=1)
+  int solve_pair = -1;  // look-ahead sequence with the trailing update applied two panels at a time: -1 = by size
+                        // (m > kPairMinM), 0 / 1 forced (SCS_SOLVE_PAIR)
   bool solve_attr_set = false;
   int p2p_capacity = -1;
   size_t sp_gram_smem = 0;
@@ -1196,6 +1198,10 @@ static int run_gram(scs_problem* p, XRef x) {
   return SCS_OK;
 }
 
+// Above this order the look-ahead Cholesky applies the trailing update two panels at a time (chol_enqueue): the
+// m x m matrix (8 m^2 bytes) no longer fits the 126 MB L2 and each pass over the trailing part is DRAM traffic.
+constexpr int kPairMinM = 4096;
+
 // Enqueues the factorisation part of run_solve (save, look-ahead or legacy Cholesky with the forward solve folded in) on
 // c->stream / c->stream2.  Capturable: no host synchronisation, the second stream forks from and re-joins the first.
 static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int* d_info, double* b, double* tmp,
@@ -1212,6 +1218,11 @@ static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int*
   if (c->solve_mode == 0) {
     // look-ahead sequence (kernels_solve.cuh): diag -> trsm on the main stream, the trailing update of step k on the
     // second stream while diag(k+1) runs; trsm(k+1) waits for it.
+    // Paired variant (large m, where the trailing matrix no longer fits the L2 and every pass over it is DRAM
+    // traffic): after an even step only the next block column receives panel k (few tiles: trsm(k+1) needs them);
+    // after the odd step k+1 the whole trailing matrix receives panels k and k+1 in ONE read-modify-write, and the
+    // diagonal block at the pair boundary applies both pending panels to its own tile.
+    const bool pair = c->solve_pair < 0 ? m > kPairMinM : c->solve_pair != 0;
     bool upd_pending = false;
     int upd_idx = 0;
     for (int k = 0; k < nblk; ++k) {
@@ -1219,8 +1230,9 @@ static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int*
       const int nb = std::min(kNB, m - k0);
       const int rem = m - k0 - nb;
       const int rb = (rem + kNB - 1) / kNB;
+      const int nprev = k == 0 ? 0 : ((pair && !(k & 1)) ? 2 : 1);
       LAUNCH(c, k_chol_diag, 1, kCholDiagThreads, kCholDiagSmem, M, (int64_t)m, m, k0, rdiag, d_info, (const double*)b,
-             tmp, (k == 1 ? d_prof : (long long*)nullptr));
+             tmp, (k == 1 ? d_prof : (long long*)nullptr), nprev);
       if (rem <= 0) break;
       if (upd_pending) {
         CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_upd[upd_idx], 0));
@@ -1228,11 +1240,14 @@ static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int*
       }
       LAUNCH(c, k_chol_trsm<false>, rb, kTrsmThreads, 0, M, (int64_t)m, m, k0, (const double*)rdiag, b,
              (const double*)tmp, (double*)nullptr, (k == 1 && d_prof ? d_prof + 11 : (long long*)nullptr));
-      const int ntiles = rb * (rb + 1) / 2 - 1;  // the first diagonal tile is k_chol_diag(k+1)'s
+      const bool colonly = pair && !(k & 1);
+      // the first diagonal tile is k_chol_diag(k+1)'s
+      const int ntiles = colonly ? rb - 1 : rb * (rb + 1) / 2 - 1;
       if (ntiles > 0) {
         CU_TRY(cudaEventRecord(c->ev_trsm[k & 1], c->stream));
         CU_TRY(cudaStreamWaitEvent(c->stream2, c->ev_trsm[k & 1], 0));
-        k_syrk_update<<<ntiles, 128, kTileSmem, c->stream2>>>(M, (int64_t)m, m, k0, ntiles, b, (const double*)tmp, 1);
+        k_syrk_update<<<ntiles, 128, kTileSmem, c->stream2>>>(M, (int64_t)m, m, k0, ntiles, b, (const double*)tmp, 1,
+                                                              (pair && (k & 1)) ? 2 : 1, colonly ? 1 : 0);
         c->launches += 1;
         CU_TRY(cudaGetLastError());
         upd_idx = k & 1;
@@ -1252,7 +1267,7 @@ static int chol_enqueue(scs_ctx* c, double* M, double* Msave, double* Linv, int*
       if (rem > 0) {
         const int ntiles = rb * (rb + 1) / 2;
         LAUNCH(c, k_syrk_update, ntiles + (rem + 127) / 128, 128, kTileSmem, M, (int64_t)m, m, k0, ntiles, b,
-               (const double*)tmp, 0);
+               (const double*)tmp, 0, 1, 0);
       }
     }
   }
@@ -1513,6 +1528,7 @@ extern "C" int scs_ctx_create(int device, int rank, int world, const void* id128
   }
   for (int i = 0; i < 5; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming));
   if (const char* e = getenv("SCS_SOLVE_LEGACY")) c->solve_mode = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SCS_SOLVE_PAIR")) c->solve_pair = atoi(e) ? 1 : 0;
   CU_TRY(cudaMalloc((void**)&c->d_flag, sizeof(double)));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;

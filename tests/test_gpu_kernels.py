@@ -180,6 +180,28 @@ def test_linear_solve_legacy_sequence(scs, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_linear_solve_paired_trailing_update(scs, monkeypatch, pair):
+    """SCS_SOLVE_PAIR forces / forbids the two-panels-at-a-time trailing update of the look-ahead Cholesky (by default
+    chosen by size: m > 4096).  Orders with an even and an odd number of 64-blocks, ragged last blocks, one to four
+    blocks; the indefinite case still reaches the LU fallback."""
+    monkeypatch.setenv("SCS_SOLVE_PAIR", pair)
+    ctx = scs.Context(0)
+    monkeypatch.delenv("SCS_SOLVE_PAIR")
+    for m in (64, 65, 128, 129, 192, 193, 256, 300, 777, 1024, 1472):
+        rng = np.random.default_rng(m)
+        B = rng.standard_normal((m + 3, m))
+        M = B.T @ B + 0.5 * np.eye(m)
+        b = rng.standard_normal(m)
+        d, fb = ctx.linear_solve(M, b)
+        assert not fb
+        assert relerr(d, np.linalg.solve(M, b)) <= 1e-11 * np.linalg.cond(M), m
+    Mi = M - 2.0 * np.diag(np.arange(m) % 2) * np.trace(M) / m
+    d2, fb2 = ctx.linear_solve(Mi, b)
+    assert fb2 and relerr(d2, np.linalg.solve(Mi, b)) <= 1e-11 * np.linalg.cond(Mi)
+    ctx.close()
+
+
 def _mk(scs, m, reg, lam, **kw):
     A = synth.make_A(8, m)
     return scs.Problem(A, np.ones(8), np.zeros(m), scs.LeastSquaresLoss(8.0), lam, **kw)
