@@ -93,3 +93,47 @@ def test_blas_thread_count_is_set_explicitly_even_under_torchrun_env():
     assert out.returncode == 0, out.stderr[-2000:]
     got, now, cores = map(int, out.stdout.split())
     assert got == now == cores or cores > 64  # OpenBLAS builds cap their pool (64 / 128 threads)
+
+
+def _chol_schedule(M, pair):
+    """numpy model of chol_enqueue's look-ahead schedule (scs_lib.cu): which kernel touches which 64-block when.
+    diag(k) applies `nprev` pending panels to its own tile and factors it; trsm(k) solves the panel below; the trailing
+    update runs with tile0 = 1 (never the first diagonal tile), either every step (pair = False) or — paired — on the
+    next block column only after even steps and on everything with both panels after odd steps."""
+    NB = 64
+    M = np.tril(M).copy()
+    m = M.shape[0]
+    nblk = (m + NB - 1) // NB
+    blk = lambda i: slice(i * NB, min(m, (i + 1) * NB))
+    for k in range(nblk):
+        nprev = 0 if k == 0 else (2 if (pair and k % 2 == 0) else 1)
+        for h in range(nprev, 0, -1):
+            P = M[blk(k), blk(k - h)]
+            M[blk(k), blk(k)] -= np.tril(P @ P.T)
+        L = np.linalg.cholesky(M[blk(k), blk(k)] + np.tril(M[blk(k), blk(k)], -1).T)
+        M[blk(k), blk(k)] = L
+        if k == nblk - 1:
+            break
+        M[(k + 1) * NB:, blk(k)] = np.linalg.solve(L, M[(k + 1) * NB:, blk(k)].T).T
+        rb = nblk - 1 - k
+        colonly = pair and k % 2 == 0
+        kpan = 2 if (pair and k % 2 == 1) else 1
+        tiles = [(ti, 0) for ti in range(1, rb)] if colonly else \
+            [(ti, tj) for ti in range(rb) for tj in range(ti + 1) if (ti, tj) != (0, 0)]
+        for ti, tj in tiles:
+            for h in range(kpan - 1, -1, -1):
+                Pi = M[blk(k + 1 + ti), blk(k - h)]
+                Pj = M[blk(k + 1 + tj), blk(k - h)]
+                upd = Pi @ Pj.T
+                M[blk(k + 1 + ti), blk(k + 1 + tj)] -= np.tril(upd) if ti == tj else upd
+    return M
+
+
+@pytest.mark.parametrize("m", [64, 65, 128, 129, 192, 200, 256, 321, 448])
+@pytest.mark.parametrize("pair", [False, True])
+def test_lookahead_cholesky_schedule_applies_every_panel_exactly_once(m, pair):
+    rng = np.random.default_rng(m)
+    B = rng.standard_normal((m + 5, m))
+    G = B.T @ B + np.eye(m)
+    L = _chol_schedule(G, pair)
+    assert np.allclose(L, np.linalg.cholesky(G), rtol=0, atol=1e-11 * np.abs(G).max())
