@@ -1058,8 +1058,24 @@ static int run_gram_i8(scs_problem* p, int* done) {
   if (pl.pchunks > p->i8_pchunks_cap) return fail(SCS_STATE_ERROR, "int8 Gram: partial-residue buffer too small");
   {
     StageTimer t(c, ST_GRAM);
+    // SCS_I8_OVERLAP_PROBE=1 (measurement only): a second k_residues launch with the same arguments (it rewrites the
+    // planes with identical bytes) runs on the second stream WHILE the SYRK runs: the `gram` stage then reports the time
+    // of the two together, i.e. what a chunk-pipelined residue pass could hide at best.
+    static const bool overlap_probe = getenv("SCS_I8_OVERLAP_PROBE") && atoi(getenv("SCS_I8_OVERLAP_PROBE"));
+    const bool probe = overlap_probe && !p->i8_signed && p->i8_nmod == 12;
+    if (probe) {
+      CU_TRY(cudaEventRecord(c->ev_trsm[0], c->stream));
+      CU_TRY(cudaStreamWaitEvent(c->stream2, c->ev_trsm[0], 0));
+      const int nblk = (int)((nproc + kWsRows - 1) / kWsRows);
+      k_residues<12, false><<<dim3((unsigned)nblk, (unsigned)std::min(m, 64)), 256, 0, c->stream2>>>(
+          p->dA + p->alo, p->ldd, nproc, m, p->dw + p->alo, p->d_colscale, p->d_planes + p->alo, p->ldx,
+          (const int64_t*)nullptr, 0, (int8_t*)nullptr, (int64_t)0);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaEventRecord(c->ev_upd[0], c->stream2));
+    }
     SCS_TRY(i8_launch_syrk(p, p->xmap, p->xmap_b, pl));
     if (cpl.nchunks > 0) SCS_TRY(i8_launch_syrk(p, p->cmap, p->cmap_b, cpl));
+    if (probe) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_upd[0], 0));
   }
   if (c->world <= 1) {
     StageTimer t(c, ST_GRAMFIN);
