@@ -106,7 +106,7 @@ def build_problem(S, wl, n_total, row0, n_local, ctx, x0):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -131,8 +131,19 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+
+        def num(col):
+            out = []
+            for r in self.rows:
+                try:
+                    out.append(float(r[col]))
+                except (IndexError, ValueError):
+                    pass
+            return out
+        pw, lim = num(2), num(7)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": float(np.median(pw)) if pw else None,
+                "power_limit_w": max(lim) if lim else None}
 
 
 def fp64_peak_tflops(torch, dev):
