@@ -137,3 +137,19 @@ def test_lookahead_cholesky_schedule_applies_every_panel_exactly_once(m, pair):
     G = B.T @ B + np.eye(m)
     L = _chol_schedule(G, pair)
     assert np.allclose(L, np.linalg.cholesky(G), rtol=0, atol=1e-11 * np.abs(G).max())
+
+
+def test_clock_sampler_parses_power_and_throttle_reasons():
+    """bench.ClockSampler: median SM clock and power, the enforced limit, and the set of active throttle reasons from
+    nvidia-smi's CSV rows ([N/A] fields and short rows are skipped, not fatal)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    c = bench.ClockSampler(0)
+    c.rows = [["1586", "1965", "987.30", "Not Active", "Not Active", "Not Active", "Active", "1000.00"],
+              ["1590", "1965", "[N/A]", "Not Active", "Not Active", "Not Active", "Active", "1000.00"],
+              ["1605", "1965", "995.10", "Not Active", "Not Active", "Not Active", "Not Active", "1000.00"],
+              ["garbage"]]
+    out = c.stop()
+    assert out["sm_mhz"] == 1590.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
+    assert abs(out["power_w"] - 991.2) < 1e-9 and out["power_limit_w"] == 1000.0
